@@ -1,0 +1,64 @@
+"""Builds liblatok_b200.so in-tree (nvcc cross-compiles sm_100a without a GPU).
+
+    python -m latok_b200.build [--verbose]
+
+The built library is git-ignored but travels with the working tree to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+LIB = PKG / "liblatok_b200.so"
+SOURCES = [CSRC / "latok_kernels.cu", CSRC / "latok_capi.cu"]
+HEADERS = [CSRC / "latok_internal.h", ROOT / "include" / "latok_b200.h"]
+GEN = CSRC / "_gen" / "latok_tables.h"
+RANGES = PKG / "data" / "ucd11_latok_classes.txt"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-shared", "-cudart", "static",
+]
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; liblatok_b200.so cannot be built (there is no CPU fallback)")
+
+
+def _stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = SOURCES + HEADERS + [RANGES, ROOT / "tools" / "gen_tables.py", Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not _stale():
+        return LIB
+    subprocess.run([sys.executable, str(ROOT / "tools" / "gen_tables.py")], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+    cmd = [find_nvcc(), *NVCC_FLAGS]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [str(s) for s in SOURCES] + ["-o", str(LIB)]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build_library(force=True, verbose="--verbose" in sys.argv or "-v" in sys.argv)
+    print(path)

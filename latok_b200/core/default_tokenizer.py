@@ -1,0 +1,122 @@
+"""The default LaTok tokenizer on the GPU (mirror of the reference's
+latok/core/default_tokenizer.py).
+
+Single-string entry points keep the reference's names, arguments and results:
+
+    gen_split_mask(m)   int8[L,25] feature matrix -> int8[L] split mask          (:113-134)
+    tokenize(text)      generator of token strings                               (:137-160)
+    featurize(text)     generator of LaToken(text, start_idx, end_idx, features)  (:163-191)
+
+and the batch entry points are the ones that make sense on a GPU: a whole list of strings (or a
+packed UTF-8 buffer + offsets) goes through one kernel pass and comes back as flat arrays.
+
+    tokenize_batch(texts)  -> list[list[str]]
+    featurize_batch(texts) -> list[list[LaToken]]
+    split_mask_batch(texts)-> list[int8 arrays]
+    batch_arrays(texts, ...) -> engine.BatchResult (splits, spans, CSR offsets, token features)
+
+Deliberate, documented deviations from the reference:
+  * Q5: token feature vectors are the sum over *all* characters of the span; the reference's
+    int8 row indices wrap/raise for positions >= 128.  Identical wherever the reference is defined.
+  * Q1: the empty string raises IndexError in the single-string functions exactly like the
+    reference (``splits[0] = 1`` on an empty array); in a batch it simply has no characters/tokens.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+
+from . import offsets as oft
+from .latok_utils import LaToken, build_combo_matrix, gen_block_mask
+from ..latok import _combine_matrix_rows, _gen_parse_matrix
+from ..engine import FEATS, MATRIX, SPANS, SPLITS, BatchResult, default_engine
+
+
+def build_split_combo_matrix():
+    """Split on whitespace, on a symbol, after a symbol, and at camelCase boundaries
+    (an upper-case letter next to a lower-case one) -- default_tokenizer.py:39-55."""
+    return build_combo_matrix([
+        [oft.SPACE_IDX], [oft.SYMBOL_IDX], [oft.PREV_SYMBOL_IDX],
+        [oft.UPPER_IDX, oft.NEXT_LOWER_IDX], [oft.UPPER_IDX, oft.PREV_LOWER_IDX],
+    ])
+
+
+def build_mask_combo_matrix():
+    """Marks that protect a whitespace-delimited block from being split: #tag @user $X ^y after a
+    space, ``.@user``, e-mail ``a@b`` and ``scheme://`` -- default_tokenizer.py:58-91."""
+    return build_combo_matrix([
+        [oft.TWITTER_IDX, oft.PREV_SPACE_IDX, oft.NEXT_ALPHA_IDX],
+        [oft.CHAR_PERIOD_IDX, oft.PREV_SPACE_IDX, oft.NEXT_AT_IDX, oft.AFTER_NEXT_ALPHA_IDX],
+        [oft.CHAR_AT_IDX, oft.PREV_ALPHA_NUM_IDX, oft.NEXT_ALPHA_NUM_IDX],
+        [oft.CHAR_COLON_IDX, oft.NEXT_SLASH_IDX, oft.AFTER_NEXT_SLASH_IDX, oft.PREV_ALPHA_IDX],
+    ])
+
+
+def build_symbol_combo_matrix():
+    """A symbol followed by whitespace still splits inside a protected block -- default_tokenizer.py:94-102."""
+    return build_combo_matrix([[oft.SYMBOL_IDX, oft.NEXT_SPACE_IDX]])
+
+
+C_SPLIT = build_split_combo_matrix()
+C_MASK = build_mask_combo_matrix()
+C_SYM = build_symbol_combo_matrix()
+
+
+def gen_split_mask(m: np.ndarray) -> np.ndarray:
+    """Feature matrix -> split mask, composed from the extension functions exactly as the
+    reference composes them (default_tokenizer.py:113-134); every array op below runs on the GPU
+    except the two int8 element-wise NumPy lines the reference also does in NumPy."""
+    feats = m.T
+    splits = _combine_matrix_rows(feats, C_SPLIT) * gen_block_mask(_combine_matrix_rows(feats, C_MASK),
+                                                                   feats[oft.SPACE_IDX])
+    splits += _combine_matrix_rows(feats, C_SYM)
+    splits[0] = 1
+    return splits
+
+
+def batch_arrays(texts: Sequence[str], splits=True, spans=True, feats=False, matrix=False, engine=None) -> BatchResult:
+    """One kernel pass over a list of strings; returns the flat result arrays."""
+    what = (SPLITS if splits else 0) | (SPANS if spans else 0) | (FEATS if feats else 0) | (MATRIX if matrix else 0)
+    return (engine or default_engine()).run(texts, what)
+
+
+def _token_texts(text: str, spans: np.ndarray) -> List[str]:
+    return [text[s:e].strip() for s, e in spans]
+
+
+def tokenize_batch(texts: Sequence[str], engine=None) -> List[List[str]]:
+    r = batch_arrays(texts, splits=False, spans=True, engine=engine)
+    return [_token_texts(t, r.string_spans(i)) for i, t in enumerate(texts)]
+
+
+def featurize_batch(texts: Sequence[str], engine=None) -> List[List[LaToken]]:
+    r = batch_arrays(texts, splits=False, spans=True, feats=True, engine=engine)
+    out = []
+    for i, t in enumerate(texts):
+        sp, ft = r.string_spans(i), r.string_feats(i)
+        out.append([LaToken(t[s:e].strip(), int(s), int(e), ft[k].copy()) for k, (s, e) in enumerate(sp)])
+    return out
+
+
+def split_mask_batch(texts: Sequence[str], engine=None) -> List[np.ndarray]:
+    r = batch_arrays(texts, splits=True, spans=False, engine=engine)
+    return [r.string_splits(i) for i in range(len(texts))]
+
+
+def tokenize(text: str):
+    """Yield the tokens of ``text`` (default_tokenizer.py:137-160)."""
+    if len(text) == 0:
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # reference: splits[0] = 1, :132
+    r = batch_arrays([text], splits=False, spans=True)
+    for s, e in r.spans:
+        yield text[s:e].strip()
+
+
+def featurize(text: str):
+    """Yield a LaToken per token of ``text`` (default_tokenizer.py:163-191)."""
+    if len(text) == 0:
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+    r = batch_arrays([text], splits=False, spans=True, feats=True)
+    for k, (s, e) in enumerate(r.spans):
+        yield LaToken(text[s:e].strip(), int(s), int(e), r.tok_feats[k].copy())

@@ -1,0 +1,109 @@
+// Internal structures shared by the kernels (latok_kernels.cu) and the C-ABI host layer (latok_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace latok {
+
+// ---- tiling geometry ------------------------------------------------------------------------
+// One CTA processes one "window" of WINB bytes: a left halo (context for the first owned
+// character), TILE owned bytes, and a right halo used for NEXT/AFTER_NEXT context and to close
+// the whitespace chunk that is still open at the end of the owned range.
+constexpr int NT = 512;                 // threads per CTA; thread t owns window bytes [32t, 32t+32)
+constexpr int NWARP = NT / 32;
+constexpr int LHALO = 32;               // thread 0
+constexpr int WINB = NT * 32;           // 16384
+constexpr int TILE = 16128;             // 126 * 128 B, threads 1..504
+constexpr int RHALO = WINB - LHALO - TILE;  // 224 B, threads 505..511
+constexpr int TRUST_MARGIN = 12;        // chars starting in the last 12 window bytes lack full forward context
+constexpr int FIRST_OWNED_THREAD = LHALO / 32;
+constexpr int END_OWNED_THREAD = (LHALO + TILE) / 32;
+
+constexpr int NFEAT = 25;
+constexpr int MAX_RULE_ROWS = 15;
+
+// packed Unicode class table blob (built by latok_capi.cu from _gen/latok_tables.h)
+struct TableLayout {
+    // byte offsets inside the blob; every section is 16-byte aligned
+    int ascii_feat;   // u16[128]
+    int class_feat;   // u16[16]
+    int stage1;       // u8[stage1_len]
+    int stage2;       // u8[stage2_len]
+    int total;        // multiple of 16
+    int stage1_len, stage2_len;
+    uint32_t low_limit;
+    uint32_t high_first, high_last, high_feat;  // the single non-empty run above low_limit
+};
+
+struct RuleSet {
+    int n_split, n_mask, n_sym;
+    int is_default;
+    uint32_t split[MAX_RULE_ROWS + 1];
+    uint32_t mask[MAX_RULE_ROWS + 1];
+    uint32_t sym[MAX_RULE_ROWS + 1];
+};
+
+// ---- decoupled look-back state ----------------------------------------------------------------
+// chain 1: character count, start of the current string, whitespace-chunk backlog function
+struct __align__(16) Chain1 {
+    unsigned long long n;    // aggregate: characters in tile | prefix: characters before the boundary
+    unsigned long long lf;   // aggregate: tile-relative index of the last string start | prefix: its global index
+    int u, v;                // backlog transfer function x -> max(x + u, v)   | prefix: (NEG, x)
+    unsigned has;            // aggregate: tile contains a string start
+    unsigned reset;          // used in registers only
+};
+// chain 2: emitted-token count and the feature sums of the token still open at the boundary
+struct __align__(16) Chain2 {
+    unsigned long long k;
+    unsigned has_split;
+    unsigned reset;
+    unsigned sums[8];        // 25 byte counters packed 4 per word (7 words used)
+};
+
+struct Result {
+    unsigned long long n_chars;
+    unsigned long long n_tokens;
+    unsigned long long walks;
+    unsigned long long ticket;   // dynamic tile counter (zeroed with the rest of the struct before each launch)
+    unsigned int error;      // bit 0: watchdog, bit 1: offsets not monotone, bit 2: token capacity exceeded
+    unsigned int abort_flag;
+};
+
+struct Params {
+    const uint8_t *in;
+    long long n_bytes;
+    const long long *offsets;   // [n_strings + 1]
+    long long n_strings;
+    const long long *tile_first_str;  // [ntiles + 1]
+    long long ntiles;
+    int8_t *splits;
+    long long *char_off;
+    int32_t *spans;
+    long long *tok_off;
+    int8_t *feats;
+    int8_t *matrix;
+    long long cap_tokens;
+    uint32_t what;
+    Chain1 *agg1, *inc1;
+    Chain2 *agg2, *inc2;
+    unsigned *status1, *status2;
+    unsigned epoch;
+    unsigned long long *ticket;
+    unsigned long long ticket_base;
+    Result *result;
+    const uint8_t *table_blob;
+    TableLayout tl;
+    RuleSet rules;
+};
+
+size_t tokenize_smem_bytes(const TableLayout &tl);
+cudaError_t launch_tile_index(const long long *offsets, long long n_strings, long long n_bytes,
+                              long long *tile_first_str, long long ntiles, Result *result, cudaStream_t s);
+cudaError_t launch_tokenize(const Params &p, int grid, cudaStream_t s);
+cudaError_t launch_block_mask(const int8_t *a1, long long s1, const int8_t *a2, long long s2, long long n,
+                              int8_t *out, unsigned char *scratch, cudaStream_t s);
+cudaError_t launch_combine_rows(const int8_t *m, long long m_rows, long long m_cols, long long stride_r,
+                                long long stride_c, const int8_t *idx, int idx_rows, int idx_cols,
+                                int8_t *out, cudaStream_t s);
+
+}  // namespace latok

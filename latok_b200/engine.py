@@ -1,0 +1,240 @@
+"""Batch front end: packs strings into (flat UTF-8 bytes, int64 offsets) and drives the C ABI.
+
+One ``Engine`` = one GPU (one ``latok_b200_engine`` handle).  All arithmetic of the tokenization
+path happens in liblatok_b200.so; this module only marshals NumPy buffers in and out.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass, field
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import FEATS, MATRIX, SPANS, SPLITS, NUM_FEATURES
+
+
+def pack_strings(texts: Sequence[str]):
+    """list[str] -> (uint8 buffer, int64 offsets[S+1]).  Lone surrogates (legal in ``str``, which is
+    what the reference reads, latok.c:47-55) are kept via 'surrogatepass'."""
+    enc = [t.encode("utf-8", "surrogatepass") for t in texts]
+    offsets = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        np.cumsum([len(b) for b in enc], out=offsets[1:])
+    buf = np.frombuffer(b"".join(enc), dtype=np.uint8)
+    return buf, offsets
+
+
+@dataclass
+class BatchResult:
+    """Arrays for one batch (any field not requested at submit is None).
+
+    splits[C] int8, char_offsets[S+1] int64, spans[T,2] int32 (string-relative, untrimmed, as in
+    LaToken.start_idx/end_idx), tok_offsets[S+1] int64, tok_feats[T,25] int8, matrix[C,25] int8.
+    """
+    n_strings: int
+    n_chars: int
+    n_tokens: int
+    splits: Optional[np.ndarray] = None
+    char_offsets: Optional[np.ndarray] = None
+    spans: Optional[np.ndarray] = None
+    tok_offsets: Optional[np.ndarray] = None
+    tok_feats: Optional[np.ndarray] = None
+    matrix: Optional[np.ndarray] = None
+    kernel_ms: float = 0.0
+    lookahead_walks: int = 0
+
+    def string_splits(self, i: int) -> np.ndarray:
+        return self.splits[self.char_offsets[i]:self.char_offsets[i + 1]]
+
+    def string_spans(self, i: int) -> np.ndarray:
+        return self.spans[self.tok_offsets[i]:self.tok_offsets[i + 1]]
+
+    def string_feats(self, i: int) -> np.ndarray:
+        return self.tok_feats[self.tok_offsets[i]:self.tok_offsets[i + 1]]
+
+    def string_matrix(self, i: int) -> np.ndarray:
+        return self.matrix[self.char_offsets[i]:self.char_offsets[i + 1]]
+
+
+class Engine:
+    """One GPU's tokenizer.  Not thread-safe; use one Engine per device and host thread."""
+
+    def __init__(self, device: int = 0, max_batch_bytes: int = 0, max_strings: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._L.latok_b200_create(device, max_batch_bytes, max_strings, C.byref(h)))
+        self._h = h
+        self.device = device
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.latok_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- rules (build_combo_matrix layout, latok_utils.py:27-56) -------------------------------
+    def set_rules(self, c_split=None, c_mask=None, c_sym=None):
+        if c_split is None and c_mask is None and c_sym is None:
+            _lib.check(self._L.latok_b200_set_rules(self._h, None, 0, 0, None, 0, 0, None, 0, 0))
+            return
+        mats = []
+        for m in (c_split, c_mask, c_sym):
+            if m is None:
+                raise ValueError("must specify split, mask and sym combo matrices")
+            m = np.ascontiguousarray(m, dtype=np.int8)
+            if m.ndim != 2:
+                raise ValueError("combo matrices must be 2d")
+            mats.append(m)
+        args = []
+        for m in mats:
+            args += [m.ctypes.data, m.shape[0], m.shape[1]]
+        _lib.check(self._L.latok_b200_set_rules(self._h, *args))
+
+    # ---- batch path ---------------------------------------------------------------------------
+    def submit(self, buf: np.ndarray, offsets: np.ndarray, what: int = SPLITS | SPANS):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        if offsets.ndim != 1 or len(offsets) < 1:
+            raise ValueError("offsets must be a 1d array with n_strings + 1 entries")
+        if int(offsets[-1]) > len(buf):
+            raise ValueError("offsets end beyond the UTF-8 buffer")
+        self._keep = (buf, offsets)
+        self._n_strings = len(offsets) - 1
+        self._what = what
+        _lib.check(self._L.latok_b200_submit(self._h, buf.ctypes.data if len(buf) else None, offsets.ctypes.data,
+                                             self._n_strings, what))
+
+    def submit_device(self, d_utf8: int, d_offsets: int, n_strings: int, n_bytes: int, what: int = SPLITS | SPANS):
+        """Text already in device memory (raw device pointers, e.g. tensor.data_ptr())."""
+        self._n_strings = n_strings
+        self._what = what
+        _lib.check(self._L.latok_b200_submit_device(self._h, d_utf8, d_offsets, n_strings, n_bytes, what))
+
+    def sizes(self):
+        c, t = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.latok_b200_sizes(self._h, C.byref(c), C.byref(t)))
+        return c.value, t.value
+
+    def fetch(self, out: Optional[BatchResult] = None) -> BatchResult:
+        n_chars, n_tokens = self.sizes()
+        S, w = self._n_strings, self._what
+        r = out or BatchResult(S, n_chars, n_tokens)
+        r.n_strings, r.n_chars, r.n_tokens = S, n_chars, n_tokens
+        if w & SPLITS:
+            r.splits = np.empty(n_chars, dtype=np.int8)
+        if w & (SPANS | FEATS):
+            r.tok_offsets = np.empty(S + 1, dtype=np.int64)
+        if w & SPANS:
+            r.spans = np.empty((n_tokens, 2), dtype=np.int32)
+        if w & FEATS:
+            r.tok_feats = np.empty((n_tokens, NUM_FEATURES), dtype=np.int8)
+        if w & MATRIX:
+            r.matrix = np.empty((n_chars, NUM_FEATURES), dtype=np.int8)
+        r.char_offsets = np.empty(S + 1, dtype=np.int64)
+
+        def ptr(a):
+            return None if a is None else a.ctypes.data
+        _lib.check(self._L.latok_b200_fetch(self._h, ptr(r.splits), ptr(r.char_offsets), ptr(r.spans),
+                                            ptr(r.tok_offsets), ptr(r.tok_feats), ptr(r.matrix)))
+        ms, walks = C.c_float(0), C.c_int64(0)
+        _lib.check(self._L.latok_b200_last_stats(self._h, C.byref(ms), C.byref(walks)))
+        r.kernel_ms, r.lookahead_walks = ms.value, walks.value
+        return r
+
+    def run(self, texts: Sequence[str], what: int = SPLITS | SPANS) -> BatchResult:
+        buf, offsets = pack_strings(texts)
+        self.submit(buf, offsets, what)
+        return self.fetch()
+
+    def run_packed(self, buf, offsets, what: int = SPLITS | SPANS) -> BatchResult:
+        self.submit(buf, offsets, what)
+        return self.fetch()
+
+    # ---- measurement hooks ---------------------------------------------------------------------
+    def timer_begin(self):
+        _lib.check(self._L.latok_b200_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float(0)
+        _lib.check(self._L.latok_b200_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        _lib.check(self._L.latok_b200_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # ---- the extension module's three functions ---------------------------------------------------
+    def gen_parse_matrix(self, text: str) -> np.ndarray:
+        b = text.encode("utf-8", "surrogatepass")
+        out = np.empty((len(text), NUM_FEATURES), dtype=np.int8)
+        n = C.c_int64(0)
+        src = np.frombuffer(b, dtype=np.uint8)
+        _lib.check(self._L.latok_b200_gen_parse_matrix(self._h, src.ctypes.data if len(b) else None, len(b),
+                                                       C.byref(n), out.ctypes.data if len(text) else None))
+        if n.value != len(text):
+            raise _lib.LatokCudaError(f"device decoded {n.value} characters, expected {len(text)}")
+        return out
+
+    def gen_block_mask(self, a1: np.ndarray, a2: np.ndarray) -> np.ndarray:
+        a1 = np.asarray(a1)
+        a2 = np.asarray(a2)
+        if a1.ndim != 1 or a2.ndim != 1:
+            raise ValueError("must specify 1d numpy array args")            # latok.c:157-160
+        if a1.size != a2.size:
+            raise ValueError("must specify 1d numpy arrays of matching length")  # latok.c:167-170
+        x1 = (a1 != 0).astype(np.int8)   # the reference only tests for non-zero (PyArray_Nonzero, latok.c:178,198)
+        x2 = (a2 != 0).astype(np.int8)
+        out = np.empty(a1.size, dtype=np.int8)
+        _lib.check(self._L.latok_b200_gen_block_mask(self._h, x1.ctypes.data, 1, x2.ctypes.data, 1, a1.size,
+                                                     out.ctypes.data))
+        return out
+
+    def combine_matrix_rows(self, m: np.ndarray, idxs: np.ndarray) -> np.ndarray:
+        m = np.asarray(m)
+        idxs = np.asarray(idxs)
+        if m.dtype != np.int8 or idxs.dtype != np.int8:
+            # the reference dereferences NULL here; the boundary validates instead
+            raise ValueError("m and idxs must be int8 arrays")
+        if m.ndim != 2 or idxs.ndim > 2 or idxs.ndim < 1:
+            raise ValueError("must specify 2d numpy array args")              # latok.c:309-312
+        if any(s < 0 for s in m.strides):
+            m = np.ascontiguousarray(m)
+        idxs = np.ascontiguousarray(idxs)
+        out = np.empty(m.shape[1], dtype=np.int8)
+        ir, ic = (idxs.shape[0], idxs.shape[1]) if idxs.ndim == 2 else (idxs.shape[0], 0)
+        if idxs.ndim == 2 and ic == 0:
+            out[:] = 0
+            return out
+        _lib.check(self._L.latok_b200_combine_matrix_rows(self._h, m.ctypes.data, m.shape[0], m.shape[1],
+                                                          m.strides[0], m.strides[1], idxs.ctypes.data, ir, ic,
+                                                          out.ctypes.data))
+        return out
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Process-wide engine used by the drop-in single-string functions."""
+    with _default_lock:
+        e = _default.get(device)
+        if e is None:
+            e = _default[device] = Engine(device)
+        return e
