@@ -172,6 +172,8 @@ static int build_table(latok_b200_engine *e)
     TableLayout &tl = e->tl;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
+    tl.lut3 = take(3 * LUT_ENTRIES * 4);
+    tl.lutv = take(256 * 4);
     tl.ascii_feat = take(128 * 2);
     tl.class_feat = take(16 * 2);
     tl.stage1 = take(LATOK_TBL_STAGE1_LEN);
@@ -186,6 +188,25 @@ static int build_table(latok_b200_engine *e)
     tl.high_last = LATOK_HIGH_RUNS[0][1];
     tl.high_feat = LATOK_HIGH_RUNS[0][2];
     std::vector<uint8_t> blob((size_t)tl.total, 0);
+    tl.high_class = 0;
+    for (uint32_t c = 0; c < 16; ++c) if (LATOK_CLASS_FEAT[c] == tl.high_feat) tl.high_class = c;
+    {
+        uint32_t *lut3 = reinterpret_cast<uint32_t *>(blob.data() + tl.lut3);
+        for (int e = 0; e < LUT_ENTRIES; ++e) {
+            const uint32_t f = e < 128 ? LATOK_ASCII_FEAT[e] : (e < 256 ? 0u : LATOK_CLASS_FEAT[e - 256]);
+            for (int k = 0; k < 3; ++k) {
+                uint32_t w = 0;
+                for (int b = 0; b < 4; ++b) w |= ((f >> (4 * k + b)) & 1u) << (8 * b);
+                lut3[k * LUT_ENTRIES + e] = w;
+            }
+        }
+        uint32_t *lutv = reinterpret_cast<uint32_t *>(blob.data() + tl.lutv);
+        for (int i = 0; i < 256; ++i) {
+            uint32_t w = 0;
+            for (int b = 0; b < 4; ++b) w |= ((((uint32_t)i >> b) & 1u) + 2u * (((uint32_t)i >> (4 + b)) & 1u)) << (8 * b);
+            lutv[i] = w;
+        }
+    }
     memcpy(blob.data() + tl.ascii_feat, LATOK_ASCII_FEAT, sizeof LATOK_ASCII_FEAT);
     memcpy(blob.data() + tl.class_feat, LATOK_CLASS_FEAT, sizeof LATOK_CLASS_FEAT);
     memcpy(blob.data() + tl.stage1, LATOK_STAGE1, sizeof LATOK_STAGE1);
@@ -321,7 +342,8 @@ static int run_device(latok_b200_engine *e)
     p.ticket = &e->d_result.p->ticket; p.ticket_base = 0;
     p.result = e->d_result.p;
     p.table_blob = e->d_table.p; p.tl = e->tl; p.rules = e->rules;
-    int grid = e->n_sm;
+    const bool words = (e->what & (LATOK_B200_FEATS | LATOK_B200_MATRIX)) != 0;
+    int grid = e->n_sm * tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words);
     if ((long long)grid > ntiles) grid = (int)ntiles;
 
     CU(cudaMemsetAsync(e->d_result.p, 0, sizeof(Result), e->stream));

@@ -8,16 +8,20 @@ namespace latok {
 // ---- tiling geometry ------------------------------------------------------------------------
 // One CTA processes one "window" of WINB bytes: a left halo (context for the first owned
 // character), TILE owned bytes, and a right halo used for NEXT/AFTER_NEXT context and to close
-// the whitespace chunk that is still open at the end of the owned range.
-constexpr int NT = 512;                 // threads per CTA; thread t owns window bytes [32t, 32t+32)
+// the whitespace chunk that is still open at the end of the owned range.  Thread t handles window
+// bytes [32t, 32t+32): thread 0 is the left halo, threads 1..END_OWNED_THREAD-1 own their bytes,
+// the remaining threads are the right halo.
+constexpr int NT = 256;                 // threads per CTA
 constexpr int NWARP = NT / 32;
 constexpr int LHALO = 32;               // thread 0
-constexpr int WINB = NT * 32;           // 16384
-constexpr int TILE = 16128;             // 126 * 128 B, threads 1..504
-constexpr int RHALO = WINB - LHALO - TILE;  // 224 B, threads 505..511
+constexpr int WINB = NT * 32;           // 8192
+constexpr int RHALO = 224;              // 7 threads
+constexpr int TILE = WINB - LHALO - RHALO;  // 7936 = 62 * 128 B
 constexpr int TRUST_MARGIN = 12;        // chars starting in the last 12 window bytes lack full forward context
 constexpr int FIRST_OWNED_THREAD = LHALO / 32;
 constexpr int END_OWNED_THREAD = (LHALO + TILE) / 32;
+constexpr int LUT_ENTRIES = 272;        // 256 byte values (>= 0x80: no features) + 16 non-ASCII classes
+constexpr int SPAN_STAGE = 1536;        // tokens staged in shared memory per tile before the coalesced write
 
 constexpr int NFEAT = 25;
 constexpr int MAX_RULE_ROWS = 15;
@@ -25,6 +29,8 @@ constexpr int MAX_RULE_ROWS = 15;
 // packed Unicode class table blob (built by latok_capi.cu from _gen/latok_tables.h)
 struct TableLayout {
     // byte offsets inside the blob; every section is 16-byte aligned
+    int lut3;         // u32[3][LUT_ENTRIES]: word k, byte b = feature 4k+b of the entry (bit 0)
+    int lutv;         // u32[256]: 4 split-mask bytes for (value bit-plane 0 nibble | bit-plane 1 nibble << 4)
     int ascii_feat;   // u16[128]
     int class_feat;   // u16[16]
     int stage1;       // u8[stage1_len]
@@ -32,7 +38,7 @@ struct TableLayout {
     int total;        // multiple of 16
     int stage1_len, stage2_len;
     uint32_t low_limit;
-    uint32_t high_first, high_last, high_feat;  // the single non-empty run above low_limit
+    uint32_t high_first, high_last, high_feat, high_class;  // the single non-empty run above low_limit
 };
 
 struct RuleSet {
@@ -96,7 +102,8 @@ struct Params {
     RuleSet rules;
 };
 
-size_t tokenize_smem_bytes(const TableLayout &tl);
+size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words);
+int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words);
 cudaError_t launch_tile_index(const long long *offsets, long long n_strings, long long n_bytes,
                               long long *tile_first_str, long long ntiles, Result *result, cudaStream_t s);
 cudaError_t launch_tokenize(const Params &p, int grid, cudaStream_t s);

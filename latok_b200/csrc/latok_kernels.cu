@@ -1,6 +1,7 @@
 // latok_kernels.cu -- sm_100a kernels for LaTok's tokenization hot path.
 //
-// One persistent kernel (tokenize_kernel) makes a single pass over the flat UTF-8 buffer:
+// One persistent kernel (tokenize_kernel) makes a single pass over the flat UTF-8 buffer (bit-plane form,
+// 32 characters per register):
 //
 //   TMA bulk copy of a 16 KB window (owned tile + halos) into shared memory
 //   phase 1  byte space : lead-byte detection, UTF-8 decode, class-table lookup (shared memory)
@@ -27,8 +28,6 @@ constexpr uint32_t FIRSTBIT = 1u << 25;   // character starts a string
 constexpr uint32_t LASTBIT = 1u << 26;    // character ends a string
 constexpr uint32_t FEATMASK = (1u << NFEAT) - 1;
 constexpr int NEG = -(1 << 28);           // "-infinity" of the (max,+) backlog functions
-constexpr int MAXC = WINB;                // at most one character per window byte
-constexpr int WORDS_LEN = 1 + MAXC + (MAXC >> 5) + 1 + 40;
 constexpr unsigned SPIN_LIMIT = 1u << 27; // watchdog for look-back spins
 
 // ---- small helpers ------------------------------------------------------------------------------
@@ -370,37 +369,49 @@ __device__ bool walk_ahead(const Params &p, const Tables &t, long long pos0, int
 }
 
 // =====================================================================================================
+// tokenize_kernel (v2, bit-plane formulation)
+//
+// Every thread owns 32 window bytes and keeps its characters as 32-bit BIT-PLANES in registers: bit j of
+// plane f = feature f of the thread's j-th character.  All per-character logic of the reference
+// (context features, the three combo-matrix rules, the block mask, split values, token flags) then runs
+// 32 characters per instruction.
+// =====================================================================================================
+enum { PL_A = 0, PL_N = 1, PL_NUM = 2, PL_LO = 3, PL_UP = 4, PL_SP = 5, PL_SY = 6, PL_TW = 7, PL_AT = 8, PL_CO = 9,
+       PL_SL = 10, PL_PE = 11 };
+
 struct SmemPlan {
-    int mbar, scal, tile, table, words, vals, startbits, leadmask, cpref, emit, tokpref, split, scratch, total;
+    int mbar, scal, tile, table, spans, startbits, leadmask, cpref, emit, tokpref, split, edge, scratch, words, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(int table_bytes)
+__host__ __device__ inline SmemPlan smem_plan(int table_bytes, bool want_words)
 {
     SmemPlan s; int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     s.mbar = take(16);
     s.scal = take(256);
-    s.tile = take(WINB + 16);
+    s.tile = take(WINB + 64);          // window bytes; re-used as the split-value staging buffer
     s.table = take(table_bytes);
-    s.words = take(WORDS_LEN * 4);
-    s.vals = take(WINB + 32);
+    s.spans = take(SPAN_STAGE * 8);
     s.startbits = take(NT * 4);
     s.leadmask = take(NT * 4);
     s.cpref = take((NT + 1) * 4);
     s.emit = take(NT * 4);
     s.tokpref = take((NT + 1) * 4);
     s.split = take(NT * 4);
+    s.edge = take(NWARP * 16 * 4);
     s.scratch = take(1024);
+    s.words = take(want_words ? (WINB + WINB / 32 + 64) * 4 : 0);
     s.total = o;
     return s;
 }
-size_t tokenize_smem_bytes(const TableLayout &tl) { return (size_t)smem_plan(tl.total).total; }
+size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words) { return (size_t)smem_plan(tl.total, want_words).total; }
 
 struct Scalars {          // block-shared scalars
     long long tile;
     unsigned long long G_in, base_in, K_in;
     int x_in, x_end;
     int agg_u, agg_v;
-    int need_walk, far;
+    int need_walk, far, slow_vals;
+    int lf_tile;
     unsigned open_has;
     unsigned open_sums[8];
     unsigned carry_sums[8];
@@ -421,60 +432,102 @@ __device__ __forceinline__ int block_excl_sum(int v, int *scratch, int &total, i
     return base + inc - v;
 }
 
-// exclusive scan of backlog functions (composition) and of "last string start" (max)
-__device__ __forceinline__ void block_excl_fn(Fn f, int lf, int *scratch, Fn &excl, int &lf_excl, Fn &total, int &lf_total,
-                                              int lane, int warp)
+// exclusive scan of backlog functions (composition)
+__device__ __forceinline__ void block_excl_fn(Fn f, int *scratch, Fn &excl, Fn &total, int lane, int warp)
 {
-    Fn inc = f; int lfi = lf;
+    Fn inc = f;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         int ou = __shfl_up_sync(0xFFFFFFFFu, inc.u, d), ov = __shfl_up_sync(0xFFFFFFFFu, inc.v, d);
-        int ol = __shfl_up_sync(0xFFFFFFFFu, lfi, d);
-        if (lane >= d) { inc = fn_compose(Fn{ou, ov}, inc); lfi = max(lfi, ol); }
+        if (lane >= d) inc = fn_compose(Fn{ou, ov}, inc);
     }
-    // exclusive within warp
     int eu = __shfl_up_sync(0xFFFFFFFFu, inc.u, 1), ev = __shfl_up_sync(0xFFFFFFFFu, inc.v, 1);
-    int el = __shfl_up_sync(0xFFFFFFFFu, lfi, 1);
     Fn wex = lane ? Fn{eu, ev} : fn_id();
-    int lex = lane ? el : -1;
-    if (lane == 31) { scratch[3 * warp] = inc.u; scratch[3 * warp + 1] = inc.v; scratch[3 * warp + 2] = lfi; }
+    if (lane == 31) { scratch[2 * warp] = inc.u; scratch[2 * warp + 1] = inc.v; }
     __syncthreads();
-    Fn base = fn_id(), tot = fn_id(); int lb = -1, lt = -1;
+    Fn base = fn_id(), tot = fn_id();
 #pragma unroll
     for (int w = 0; w < NWARP; ++w) {
-        Fn t = Fn{scratch[3 * w], scratch[3 * w + 1]}; int l = scratch[3 * w + 2];
-        if (w < warp) { base = fn_compose(base, t); lb = max(lb, l); }
-        tot = fn_compose(tot, t); lt = max(lt, l);
+        Fn t = Fn{scratch[2 * w], scratch[2 * w + 1]};
+        if (w < warp) base = fn_compose(base, t);
+        tot = fn_compose(tot, t);
     }
     __syncthreads();
     excl = fn_compose(base, wex);
-    lf_excl = max(lb, lex);
-    total = tot; lf_total = lt;
+    total = tot;
 }
 
-__global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
+// LUT entry (256 + class) of the multi-byte character whose lead byte is p[0] >= 0xC0
+__device__ __forceinline__ uint32_t mb_entry(const uint8_t *p, const Tables &t, uint32_t high_class)
+{
+    const uint32_t b0 = p[0];
+    if (b0 >= 0xF8u) return 256u;  // invalid lead: class 0 (no features)
+    uint32_t cp;
+    if (b0 < 0xE0u) cp = ((b0 & 0x1Fu) << 6) | (p[1] & 0x3Fu);
+    else if (b0 < 0xF0u) cp = ((b0 & 0x0Fu) << 12) | ((p[1] & 0x3Fu) << 6) | (p[2] & 0x3Fu);
+    else cp = ((b0 & 0x07u) << 18) | ((p[1] & 0x3Fu) << 12) | ((p[2] & 0x3Fu) << 6) | (p[3] & 0x3Fu);
+    if (cp < 0x80u) return cp;     // over-long form of an ASCII character
+    if (cp < t.low_limit) {
+        const uint32_t blk = t.stage1[cp >> 7];
+        const uint32_t b = t.stage2[blk * 64u + ((cp & 127u) >> 1)];
+        return 256u + ((cp & 1u) ? (b >> 4) : (b & 15u));
+    }
+    return (cp >= t.high_first && cp <= t.high_last) ? 256u + high_class : 256u;
+}
+
+// 4x4 byte transpose: four accumulators (8 characters each, one byte per feature) -> four 32-character planes
+__device__ __forceinline__ void planes4(const uint32_t a[4], uint32_t &p0, uint32_t &p1, uint32_t &p2, uint32_t &p3)
+{
+    const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[0], a[1], 0x7362);
+    const uint32_t t2 = __byte_perm(a[2], a[3], 0x5140), t3 = __byte_perm(a[2], a[3], 0x7362);
+    p0 = __byte_perm(t0, t2, 0x5410); p1 = __byte_perm(t0, t2, 0x7632);
+    p2 = __byte_perm(t1, t3, 0x5410); p3 = __byte_perm(t1, t3, 0x7632);
+}
+
+// In-register 32x32 bit-matrix transpose: planes (bit j of a[f]) -> per-character words (bit f of a[j])
+__device__ __forceinline__ void transpose32(uint32_t a[32])
+{
+#pragma unroll
+    for (int j = 16, sh = 0; j != 0; j >>= 1, ++sh) {
+        const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if ((k & j) == 0) {
+                const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+                a[k] ^= t << j;
+                a[k + j] ^= t;
+            }
+        }
+    }
+}
+
+template <bool kDefault, bool kWords>
+__global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemPlan sp = smem_plan(p.tl.total);
+    const SmemPlan sp = smem_plan(p.tl.total, kWords);
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.mbar);
     Scalars &sc = *reinterpret_cast<Scalars *>(smem + sp.scal);
     uint8_t *tileS = smem + sp.tile;
+    uint8_t *valS = smem + sp.tile;      // aliases the window bytes (dead after phase 1)
     uint8_t *tableS = smem + sp.table;
-    uint32_t *wordS = reinterpret_cast<uint32_t *>(smem + sp.words);
-    uint8_t *valS = smem + sp.vals;
+    int32_t *spanS = reinterpret_cast<int32_t *>(smem + sp.spans);
     uint32_t *startbits = reinterpret_cast<uint32_t *>(smem + sp.startbits);
     uint32_t *leadmaskS = reinterpret_cast<uint32_t *>(smem + sp.leadmask);
     int *cprefS = reinterpret_cast<int *>(smem + sp.cpref);
     uint32_t *emitS = reinterpret_cast<uint32_t *>(smem + sp.emit);
     int *tokprefS = reinterpret_cast<int *>(smem + sp.tokpref);
     uint32_t *splitS = reinterpret_cast<uint32_t *>(smem + sp.split);
+    uint32_t *edgeS = reinterpret_cast<uint32_t *>(smem + sp.edge);
     int *scratch = reinterpret_cast<int *>(smem + sp.scratch);
+    uint32_t *wordS = reinterpret_cast<uint32_t *>(smem + sp.words);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
 
     if (ld_volatile_u32(&p.result->error) & 2u) return;  // offsets failed validation in tile_index_kernel
 
-    // one-time per CTA: class table into shared memory, mbarrier init
+    // one-time per CTA: tables into shared memory, mbarrier init
     for (int i = tid; i < p.tl.total / 16; i += NT)
         reinterpret_cast<uint4 *>(tableS)[i] = __ldg(reinterpret_cast<const uint4 *>(p.table_blob) + i);
     if (tid == 0) mbar_init(mbar, 1);
@@ -485,6 +538,9 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
     tb.stage1 = tableS + p.tl.stage1;
     tb.stage2 = tableS + p.tl.stage2;
     tb.low_limit = p.tl.low_limit; tb.high_first = p.tl.high_first; tb.high_last = p.tl.high_last; tb.high_feat = p.tl.high_feat;
+    const uint32_t *lut0 = reinterpret_cast<const uint32_t *>(tableS + p.tl.lut3);
+    const uint32_t *lut1 = lut0 + LUT_ENTRIES, *lut2 = lut1 + LUT_ENTRIES;
+    const uint32_t *lutv = reinterpret_cast<const uint32_t *>(tableS + p.tl.lutv);
 
     uint32_t phase = 0;
     const bool want_feats = (p.what & 4u) != 0u, want_matrix = (p.what & 8u) != 0u;
@@ -496,7 +552,7 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
         const long long tile = sc.tile;
         if (tile >= p.ntiles) break;
 
-        // ------------------------------------------------------------------ load window
+        // ------------------------------------------------------------------ load window (TMA bulk copy)
         const long long w0 = tile * (long long)TILE - LHALO;
         const long long lo = w0 < 0 ? 0 : w0;
         long long hi = w0 + WINB;
@@ -518,7 +574,7 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
             }
         }
         startbits[tid] = 0;
-        if (tid == 0) { sc.need_walk = 0; sc.far = 0; sc.open_has = 0; }
+        if (tid == 0) { sc.need_walk = 0; sc.far = 0; sc.open_has = 0; sc.slow_vals = 0; }
         __syncthreads();  // (B)
         {
             const long long wend = w0 + WINB;
@@ -532,44 +588,108 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
         if (tma_bytes > 0) { mbar_wait(mbar, phase); phase ^= 1u; }
         __syncthreads();  // (C)
 
-        // ------------------------------------------------------------------ phase 1: bytes -> characters
+        // ------------------------------------------------------------------ phase 1: bytes -> bit-planes
         const int wb0 = tid * 32;
-        uint32_t lead;
         const uint32_t sb = startbits[tid];
+        uint32_t lead, mbl;          // lead bytes / lead bytes of multi-byte characters (byte positions)
+        int vhi;                     // number of valid bytes at the low end of this thread's range
+        uint32_t acc0[4], acc1[4], acc2[4];
         {
             const uint4 q0 = *reinterpret_cast<const uint4 *>(tileS + wb0);
             const uint4 q1 = *reinterpret_cast<const uint4 *>(tileS + wb0 + 16);
             const uint32_t wds[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            uint32_t leadbits = 0;
+            uint32_t leadbits = 0, hib = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 uint32_t t = (wds[j] & 0xC0C0C0C0u) ^ 0x80808080u;   // byte == 0  <=>  continuation byte
                 uint32_t m = (t | (t << 1)) & 0x80808080u;
                 leadbits |= (((m >> 7) * 0x10204080u) >> 28) << (4 * j);
+                hib |= ((((wds[j] & 0x80808080u) >> 7) * 0x10204080u) >> 28) << (4 * j);
             }
             const long long g0 = w0 + wb0;
             const int vlo = g0 < 0 ? int(-g0 < 32 ? -g0 : 32) : 0;
             const long long rem = p.n_bytes - g0;
-            const int vhi = rem <= 0 ? 0 : (rem >= 32 ? 32 : int(rem));
+            vhi = rem <= 0 ? 0 : (rem >= 32 ? 32 : int(rem));
             const uint32_t valid = vhi > vlo ? (mask_lt(vhi) & ~mask_lt(vlo)) : 0u;
             lead = (leadbits & valid) | sb;
-        }
-        int c_end;
-        const int c0 = block_excl_sum(__popc(lead), scratch, c_end, lane, warp);
-        leadmaskS[tid] = lead;
-        cprefS[tid] = c0;
-        if (tid == 0) { cprefS[NT] = c_end; wordS[widx(-1)] = 0; }
-        {
-            uint32_t mm = lead; int c = c0;
-            while (mm) {
-                int k = __ffs(mm) - 1; mm &= mm - 1;
-                uint32_t f = classify_at(tileS + wb0 + k, tb);
-                if ((sb >> k) & 1u) f |= FIRSTBIT;
-                wordS[widx(c)] = f; ++c;
+            mbl = leadbits & hib & valid;     // bytes >= 0xC0 inside the data
+            // every byte through the feature LUT (bytes >= 0x80 and padding map to "no features")
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t b = (wds[2 * g + (j >> 2)] >> ((j & 3) * 8)) & 0xFFu;
+                    a0 += lut0[b] << j; a1 += lut1[b] << j; a2 += lut2[b] << j;
+                }
+                acc0[g] = a0; acc1[g] = a1; acc2[g] = a2;
             }
         }
-        if (tid < 36) wordS[widx(c_end + tid)] = 0;
-        __syncthreads();  // (D)
+        // patch in the multi-byte characters (decode + two-stage class table)
+        {
+            uint32_t mm = mbl;
+            while (mm) {
+                const int k = __ffs(mm) - 1; mm &= mm - 1;
+                const uint32_t e = mb_entry(tileS + wb0 + k, tb, p.tl.high_class);
+                const uint32_t x0 = lut0[e] << (k & 7), x1 = lut1[e] << (k & 7), x2 = lut2[e] << (k & 7);
+                const int g = k >> 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (g == q) { acc0[q] |= x0; acc1[q] |= x1; acc2[q] |= x2; }
+            }
+        }
+        uint32_t P[12];
+        planes4(acc0, P[0], P[1], P[2], P[3]);
+        planes4(acc1, P[4], P[5], P[6], P[7]);
+        planes4(acc2, P[8], P[9], P[10], P[11]);
+        uint32_t Fm = sb;
+        // byte space -> character space: squeeze out the continuation-byte positions
+        {
+            uint32_t del = lead ? (~lead & mask_lt(vhi)) : 0u;
+#pragma unroll
+            for (int f = 0; f < 12; ++f) P[f] &= lead;
+            while (del) {
+                const int top = 31 - __clz(del);
+                const int r = __clz(~(del << (31 - top)));       // run length of deleted bytes ending at `top`
+                const int c = top - r;                            // last kept position below the run (may be -1)
+                const uint32_t keep = mask_lt(c + 1);
+#pragma unroll
+                for (int f = 0; f < 12; ++f) P[f] = (P[f] & keep) | ((P[f] >> r) & ~keep);
+                Fm = (Fm & keep) | ((Fm >> r) & ~keep);
+                del &= keep;
+            }
+        }
+        const int n = __popc(lead);                     // characters of this thread (incl. the end-of-data terminator)
+        int c_end;
+        const int c0 = block_excl_sum(n, scratch, c_end, lane, warp);
+        leadmaskS[tid] = lead;
+        cprefS[tid] = c0;
+        if (tid == 0) cprefS[NT] = c_end;
+
+        // ------------------------------------------------------------------ phase 2a: context planes
+        // prev: last character of the previous thread; next/after-next: first two characters of the next thread
+        const uint32_t myLB = n > 0 ? ((((P[PL_A] >> (n - 1)) & 1u)) | (((P[PL_N] >> (n - 1)) & 1u) << 1) |
+                                       (((P[PL_LO] >> (n - 1)) & 1u) << 2) | (((P[PL_SP] >> (n - 1)) & 1u) << 3) |
+                                       (((P[PL_SY] >> (n - 1)) & 1u) << 4) | 32u)
+                                    : 0u;
+        uint32_t LB = __shfl_up_sync(FULL, myLB, 1);
+        uint32_t XA = __shfl_down_sync(FULL, P[PL_A], 1), XN = __shfl_down_sync(FULL, P[PL_N], 1);
+        uint32_t XLO = __shfl_down_sync(FULL, P[PL_LO], 1), XSP = __shfl_down_sync(FULL, P[PL_SP], 1);
+        uint32_t XAT = __shfl_down_sync(FULL, P[PL_AT], 1), XSL = __shfl_down_sync(FULL, P[PL_SL], 1);
+        uint32_t XF = __shfl_down_sync(FULL, Fm, 1);
+        if (lane == 0) {
+            uint32_t *e = edgeS + warp * 16;
+            e[0] = P[PL_A]; e[1] = P[PL_N]; e[2] = P[PL_LO]; e[3] = P[PL_SP]; e[4] = P[PL_AT]; e[5] = P[PL_SL]; e[6] = Fm;
+        }
+        if (lane == 31) edgeS[warp * 16 + 8] = myLB;
+        __syncthreads();  // (D) edges + cpref/leadmask visible
+        if (lane == 31) {
+            if (warp + 1 < NWARP) {
+                const uint32_t *e = edgeS + (warp + 1) * 16;
+                XA = e[0]; XN = e[1]; XLO = e[2]; XSP = e[3]; XAT = e[4]; XSL = e[5]; XF = e[6];
+            } else { XA = XN = XLO = XSP = XAT = XSL = XF = 0; }
+        }
+        if (lane == 0) LB = warp > 0 ? edgeS[(warp - 1) * 16 + 8] : 0u;
 
         auto cidx = [&](int wb) -> int {  // characters starting at window bytes < wb
             int t = wb >> 5;
@@ -581,69 +701,148 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
         if (own_end_g > p.n_bytes) own_end_g = p.n_bytes;
         const int c_hi = cidx(int(own_end_g - w0));
         const bool term_in_win = p.n_bytes < w0 + WINB;
-        const int c_trust = term_in_win ? cidx(int(p.n_bytes - w0)) : cidx(WINB - TRUST_MARGIN);
         const int n_own = c_hi - c_lo;
+        // thread-local masks: real characters (not the terminator), owned, active (trusted forward context)
+        const long long g0 = w0 + wb0;
+        const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
+        const uint32_t REAL = mask_lt(n - (has_term ? 1 : 0));
+        const uint32_t OWN = (tid >= FIRST_OWNED_THREAD && tid < END_OWNED_THREAD) ? REAL : 0u;
+        uint32_t ACT = tid >= FIRST_OWNED_THREAD ? REAL : 0u;
+        if (tid == NT - 1 && !term_in_win) ACT &= mask_lt(__popc(lead & mask_lt(32 - TRUST_MARGIN)));
 
-        // ------------------------------------------------------------------ phase 2a: context + rules
-        const int cb = tid * 32;
-        const uint32_t ACT = range_mask(cb, c_lo, c_trust), OWN = range_mask(cb, c_lo, c_hi);
-        uint32_t r[36];
+        // 64-bit view "this thread's characters followed by the next thread's": shift right by 1 / 2
+        auto next1 = [&](uint32_t X, uint32_t Xn) -> uint32_t {
+            const uint32_t l = X | __funnelshift_lc(0u, Xn, n), h = __funnelshift_lc(Xn, 0u, n);
+            return __funnelshift_r(l, h, 1);
+        };
+        auto next2 = [&](uint32_t X, uint32_t Xn) -> uint32_t {
+            const uint32_t l = X | __funnelshift_lc(0u, Xn, n), h = __funnelshift_lc(Xn, 0u, n);
+            return __funnelshift_r(l, h, 2);
+        };
+        const uint32_t Lm_raw = next1(Fm, XF);           // character ends a string (next one starts a string)
+        const uint32_t L2m = next2(Fm, XF);
+        const uint32_t nF = ~Lm_raw, aF = ~(Lm_raw | L2m), pF = ~Fm;
+        uint32_t full[25];
 #pragma unroll
-        for (int j = 0; j < 36; ++j) r[j] = wordS[widx(cb - 1 + j)];
-        uint32_t Sraw = 0, Mm = 0, Fm = 0, Lm = 0;
-        uint32_t pk[8];
+        for (int f = 0; f < 12; ++f) full[f] = P[f];
+        full[12] = ((P[PL_A] << 1) | (LB & 1u)) & pF;                 // PREV_ALPHA
+        full[13] = next1(P[PL_A], XA) & nF;                           // NEXT_ALPHA
+        full[14] = ((P[PL_N] << 1) | ((LB >> 1) & 1u)) & pF;          // PREV_ALPHA_NUM
+        full[15] = next1(P[PL_N], XN) & nF;                           // NEXT_ALPHA_NUM
+        full[16] = ((P[PL_LO] << 1) | ((LB >> 2) & 1u)) & pF;         // PREV_LOWER
+        full[17] = next1(P[PL_LO], XLO) & nF;                         // NEXT_LOWER
+        full[18] = ((P[PL_SP] << 1) | ((LB >> 3) & 1u)) | Fm;         // PREV_SPACE  (start of string = space)
+        full[19] = next1(P[PL_SP], XSP) | Lm_raw;                     // NEXT_SPACE  (end of string = space)
+        full[20] = ((P[PL_SY] << 1) | ((LB >> 4) & 1u)) & pF;         // PREV_SYMBOL
+        full[21] = next1(P[PL_AT], XAT) & nF;                         // NEXT_AT
+        full[22] = next1(P[PL_SL], XSL) & nF;                         // NEXT_SLASH
+        full[23] = next2(P[PL_A], XA) & aF;                           // AFTER_NEXT_ALPHA
+        full[24] = next2(P[PL_SL], XSL) & aF;                         // AFTER_NEXT_SLASH
+
+        // ---- rules: split count, mark, sym (combine_matrix_rows 2-D, latok.c:318-341) as bit-sliced counters
+        uint32_t CNT[4], SYC[4], Mm;
+        if (kDefault) {
+            // C_SPLIT: SPACE + SYMBOL + PREV_SYMBOL + UPPER*NEXT_LOWER + UPPER*PREV_LOWER (default_tokenizer.py:49-55)
+            const uint32_t t1 = full[5], t2 = full[6], t3 = full[20], t4 = full[4] & full[17], t5 = full[4] & full[16];
+            const uint32_t s1 = t1 ^ t2 ^ t3, c1 = (t1 & t2) | (t3 & (t1 ^ t2));
+            const uint32_t s2 = t4 ^ t5, c2 = t4 & t5;
+            CNT[0] = s1 ^ s2;
+            const uint32_t c3 = s1 & s2;
+            CNT[1] = c1 ^ c2 ^ c3;
+            CNT[2] = (c1 & c2) | (c3 & (c1 ^ c2));
+            CNT[3] = 0;
+            // C_MASK (default_tokenizer.py:80-91)
+            Mm = (full[7] & full[18] & full[13]) | (full[11] & full[18] & full[21] & full[23]) |
+                 (full[8] & full[14] & full[15]) | (full[9] & full[22] & full[24] & full[12]);
+            // C_SYM: SYMBOL*NEXT_SPACE (default_tokenizer.py:100-102)
+            SYC[0] = full[6] & full[19]; SYC[1] = SYC[2] = SYC[3] = 0;
+        } else {
+            auto term = [&](uint32_t mask) -> uint32_t {
+                uint32_t a = 0xFFFFFFFFu;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pk[j] = 0;
+                for (int f = 0; f < NFEAT; ++f) a &= full[f] | (((mask >> f) & 1u) - 1u);
+                return a;
+            };
+            auto add1 = [&](uint32_t c[4], uint32_t t) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const uint32_t w = r[i + 1];
-            const bool F = (w & FIRSTBIT) != 0u, L = (r[i + 2] & FIRSTBIT) != 0u, L2 = (r[i + 3] & FIRSTBIT) != 0u;
-            uint32_t full = make_word(r[i], w, r[i + 2], r[i + 3], F, L, L2);
-            uint32_t cnt, sy; bool mk;
-            eval_rules(p.rules, full, cnt, mk, sy);
-            const uint32_t bit = 1u << i;
-            if (full & (1u << 5)) Sraw |= bit;
-            if (mk) Mm |= bit;
-            if (F) Fm |= bit;
-            if (L) Lm |= bit;
-            pk[i >> 2] |= ((cnt & 15u) | ((sy & 15u) << 4)) << ((i & 3) * 8);
-            r[i + 1] = full | (F ? FIRSTBIT : 0u) | (L ? LASTBIT : 0u);
+                for (int b = 0; b < 4; ++b) { const uint32_t k = c[b] & t; c[b] ^= t; t = k; }
+            };
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { CNT[b] = 0; SYC[b] = 0; }
+            Mm = 0;
+            for (int i = 0; i < p.rules.n_split; ++i) add1(CNT, term(p.rules.split[i]));
+            for (int i = 0; i < p.rules.n_mask; ++i) Mm |= term(p.rules.mask[i]);
+            for (int i = 0; i < p.rules.n_sym; ++i) add1(SYC, term(p.rules.sym[i]));
         }
+        const uint32_t Sraw = P[PL_SP];
         const uint32_t S = Sraw & ACT;
-        Mm &= ACT; Fm &= ACT; Lm &= ACT;
+        Mm &= ACT;
+        const uint32_t FmA = Fm & ACT, Lm = Lm_raw & ACT;
+
+        if (kWords) {
+            // per-character 25-bit words (+ FIRST / LAST flags) for the token-feature and matrix emitters
+            uint32_t a[32];
+#pragma unroll
+            for (int f = 0; f < 25; ++f) a[f] = full[f];
+            a[25] = Fm; a[26] = Lm_raw;
+#pragma unroll
+            for (int f = 27; f < 32; ++f) a[f] = 0;
+            transpose32(a);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < n) wordS[widx(c0 + j)] = a[j];
+        }
 
         // local backlog function: +1 per mark, max(x-1,0) per space, reset at a string start
-        auto build_fn = [&](uint32_t ev) -> Fn {
-            Fn f = fn_id();
-            while (ev) {
-                const uint32_t b = ev & (0u - ev); ev &= ev - 1;
-                if (Fm & b) { f.u = NEG; f.v = 0; }
-                if (Mm & b) { f.u = max(f.u + 1, NEG); f.v = f.v + 1; }
-                if (S & b) { f.u = max(f.u - 1, NEG); f.v = max(f.v - 1, 0); }
+        Fn f_act;
+        {
+            const uint32_t ev0 = Mm | FmA;
+            if (ev0 == 0u) { f_act.u = -__popc(S); f_act.v = 0; }
+            else {
+                f_act = fn_id();
+                uint32_t ev = ev0 | S;
+                while (ev) {
+                    const uint32_t b = ev & (0u - ev); ev &= ev - 1;
+                    if (FmA & b) { f_act.u = NEG; f_act.v = 0; }
+                    if (Mm & b) { f_act.u = max(f_act.u + 1, NEG); f_act.v = f_act.v + 1; }
+                    if (S & b) { f_act.u = max(f_act.u - 1, NEG); f_act.v = max(f_act.v - 1, 0); }
+                }
             }
-            return f;
-        };
-        const uint32_t EV = Mm | S | Fm;
-        const Fn f_own = build_fn(EV & OWN);
-        const Fn f_act = fn_compose(f_own, build_fn(EV & ~OWN));
-        const uint32_t FO = Fm & OWN;
-        const int lf_own = FO ? cb + 31 - __clz(FO) : -1;
-        Fn excl, total; int lf_excl, lf_total;
-        block_excl_fn(f_act, lf_own, scratch, excl, lf_excl, total, lf_total, lane, warp);
-        if (n_own > 0 && tid == ((c_hi - 1) >> 5)) { Fn a = fn_compose(excl, f_own); sc.agg_u = a.u; sc.agg_v = a.v; }
-        if (n_own == 0 && tid == 0) { sc.agg_u = 0; sc.agg_v = NEG; }
-        if (want_feats || want_matrix) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) wordS[widx(cb + i)] = r[i + 1];
+        }
+        Fn excl, total;
+        block_excl_fn(f_act, scratch, excl, total, lane, warp);
+        if (tid == END_OWNED_THREAD) { sc.agg_u = excl.u; sc.agg_v = excl.v; }  // composition over the owned threads
+        // last string start among the owned characters (tile-relative), and for each thread the latest one before it
+        int lf_excl;
+        {
+            const uint32_t FO = Fm & OWN;
+            const int mine = FO ? c0 + 31 - __clz(FO) : -1;
+            const unsigned has = __ballot_sync(FULL, FO != 0u);
+            const unsigned below = has & mask_lt(lane);
+            const int src = below ? 31 - __clz(below) : 0;
+            const int got = __shfl_sync(FULL, mine, src);
+            lf_excl = below ? got : -1;
+            const int wlast = __shfl_sync(FULL, mine, has ? 31 - __clz(has) : 0);
+            if (lane == 0) scratch[128 + warp] = has ? wlast : -1;
         }
         __syncthreads();  // (E)
+        {
+            int lfw = -1, lft = -1;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) { const int v = scratch[128 + w]; if (w < warp) lfw = max(lfw, v); lft = max(lft, v); }
+            lf_excl = max(lf_excl, lfw);
+            if (tid == 0) sc.lf_tile = lft;
+        }
 
         // ------------------------------------------------------------------ chain 1
         if (warp == 0) {
+            int lft = -1;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) lft = max(lft, scratch[128 + w]);
             Chain1 a;
             a.n = (unsigned long long)n_own;
-            a.has = lf_total >= 0 ? 1u : 0u;
-            a.lf = a.has ? (unsigned long long)(lf_total - c_lo) : 0ull;
+            a.has = lft >= 0 ? 1u : 0u;
+            a.lf = a.has ? (unsigned long long)(lft - c_lo) : 0ull;
             a.u = sc.agg_u; a.v = sc.agg_v; a.reset = 0;
             if (lane == 0) publish(p.agg1 + tile, p.status1 + tile, a, p.epoch, 1u);
             Chain1 pre = lookback<Chain1>(tile, p.status1, p.agg1, p.inc1, p.epoch, p.result, lane);
@@ -663,10 +862,10 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
         const uint32_t CL = S | Lm;        // characters that close a whitespace chunk
         uint32_t HOT = 0;                  // closers whose chunk is blanked (backlog >= 1 at the closer)
         if (x_t != 0 || Mm != 0u) {
-            int x = x_t; uint32_t ev = EV | Lm;
+            int x = x_t; uint32_t ev = Mm | S | FmA | Lm;
             while (ev) {
                 const uint32_t b = ev & (0u - ev); ev &= ev - 1;
-                if (Fm & b) x = 0;
+                if (FmA & b) x = 0;
                 if (Mm & b) ++x;
                 if ((CL & b) && x >= 1) HOT |= b;
                 if (S & b) x = max(x - 1, 0);
@@ -685,7 +884,7 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
         const bool firstHot = hasCL && (HOT & (CL & (0u - CL))) != 0u;
         int cin;
         {
-            const unsigned H = __ballot_sync(0xFFFFFFFFu, hasCL), FH = __ballot_sync(0xFFFFFFFFu, firstHot);
+            const unsigned H = __ballot_sync(FULL, hasCL), FH = __ballot_sync(FULL, firstHot);
             if (lane == 0) { scratch[64 + 2 * warp] = H != 0u; scratch[64 + 2 * warp + 1] = H ? ((FH >> (__ffs(H) - 1)) & 1u) : 0u; }
             __syncthreads();  // (G)
             const unsigned above = lane == 31 ? 0u : (H & (0xFFFFFFFFu << (lane + 1)));
@@ -696,8 +895,10 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
                     if (scratch[64 + 2 * w2]) { cin = scratch[64 + 2 * w2 + 1]; break; }
             }
         }
-        if (n_own > 0 && tid == ((c_hi - 1) >> 5)) {
-            const bool open = (CL & (0xFFFFFFFFu << ((c_hi - 1) & 31))) == 0u && cin == 2;
+        // the whitespace chunk open at the end of the owned range: closed inside the halo, or walk ahead
+        if (tid == END_OWNED_THREAD - 1 && !term_in_win) {
+            const int nr = __popc(ACT);
+            const bool open = nr > 0 && ((CL >> (nr - 1)) & 1u) == 0u && cin == 2;
             if (open) sc.need_walk = 1;
         }
         __syncthreads();  // (H)
@@ -715,26 +916,24 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
         }
 
         // ------------------------------------------------------------------ phase 3: split values, token flags
-        uint32_t SPLIT = 0;
+        // splits = split_cnt * block_mask + sym; splits[0] = 1   (default_tokenizer.py:121-132), bit-sliced
+        const uint32_t keepm = ~Zm | Sraw;             // block mask = 1
+        uint32_t V[5];
         {
-            uint32_t vals[8];
+            uint32_t carry = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const uint32_t bit = 1u << i;
-                const uint32_t e8 = (pk[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-                const uint32_t cnt = e8 & 15u, sy = e8 >> 4;
-                // splits = split_cnt * block_mask + sym; splits[0] = 1   (default_tokenizer.py:121-132)
-                const bool blank = (Zm & bit) && !(Sraw & bit);
-                uint32_t v = ((blank ? 0u : cnt) + sy) & 0xFFu;
-                if (Fm & bit) v = 1u;
-                if (v) SPLIT |= bit;
-                if ((i & 3) == 0) vals[i >> 2] = 0;
-                vals[i >> 2] |= v << ((i & 3) * 8);
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t x = CNT[b] & keepm, y = SYC[b];
+                V[b] = x ^ y ^ carry;
+                carry = (x & y) | (carry & (x ^ y));
             }
-            *reinterpret_cast<uint4 *>(valS + cb) = make_uint4(vals[0], vals[1], vals[2], vals[3]);
-            *reinterpret_cast<uint4 *>(valS + cb + 16) = make_uint4(vals[4], vals[5], vals[6], vals[7]);
+            V[4] = carry;
+            V[0] |= Fm;
+#pragma unroll
+            for (int b = 1; b < 5; ++b) V[b] &= ~Fm;
         }
-        const uint32_t PS = (Sraw << 1) | ((r[0] >> 5) & 1u);            // previous character is a space
+        const uint32_t SPLIT = V[0] | V[1] | V[2] | V[3] | V[4];
+        const uint32_t PS = (Sraw << 1) | ((LB >> 3) & 1u);                // previous character is a space
         const uint32_t E = ((SPLIT & ~Sraw) | (~SPLIT & PS & ~Fm)) & OWN;  // a token is counted at this character
         const uint32_t EW = SPLIT & ~Fm & ~PS & OWN;                       // this split ends the previous token
         const uint32_t EL = Lm & ~Sraw & OWN;                              // end of string ends the last token
@@ -742,9 +941,94 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
         const int tp = block_excl_sum(__popc(E), scratch, ntok_tile, lane, warp);
         emitS[tid] = E; tokprefS[tid] = tp; splitS[tid] = SPLIT;
         if (tid == 0) tokprefS[NT] = ntok_tile;
+
+        // split values -> bytes -> staging buffer at (tile-relative character index + G_in % 16), so that the
+        // staging buffer and the global split mask share their 16-byte alignment
+        const int a16 = int(G_in & 15ull);
+        if (want_splits) {
+            uint32_t W[8];
+            if (kDefault) {
+                const uint32_t qlo = (V[0] & 0x0F0F0F0Fu) | ((V[1] & 0x0F0F0F0Fu) << 4);
+                const uint32_t qhi = ((V[0] >> 4) & 0x0F0F0F0Fu) | (V[1] & 0xF0F0F0F0u);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    W[2 * g] = lutv[(qlo >> (8 * g)) & 0xFFu];
+                    W[2 * g + 1] = lutv[(qhi >> (8 * g)) & 0xFFu];
+                }
+                if (V[2]) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) W[g] += spread4((V[2] >> (4 * g)) & 15u) << 2;
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int b = 0; b < 5; ++b) w += spread4((V[b] >> (4 * g)) & 15u) << b;
+                    W[g] = w;
+                }
+            }
+            // the 4 bytes before this thread's first character (tail of the previous thread)
+            uint32_t tailw = 0;
+            {
+                const int nr = n;   // terminator value bytes are harmless: they are never copied out
+                if (nr >= 4) {
+                    const int sft = nr - 4;
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int b = 0; b < 5; ++b) w += spread4((V[b] >> sft) & 15u) << b;
+                    tailw = w;
+                }
+            }
+            uint32_t headw = __shfl_up_sync(FULL, tailw, 1);
+            if (lane == 31) edgeS[warp * 16 + 9] = tailw;
+            const bool shortn = (n < 4) && (tid >= FIRST_OWNED_THREAD - 1) && (tid <= END_OWNED_THREAD) && g0 < p.n_bytes && g0 + 32 > 0;
+            const int slow = __syncthreads_or(shortn ? 1 : 0);  // (I0) also publishes edgeS[..+9]
+            if (lane == 0) headw = warp > 0 ? edgeS[(warp - 1) * 16 + 9] : 0u;
+            const int o = c0 - c_lo + a16;                 // staging offset of this thread's first character
+            if (tid >= FIRST_OWNED_THREAD && tid <= END_OWNED_THREAD && o >= 0) {
+                if (!slow) {
+                    // words are written by the thread that owns their LAST byte: no partial words, no races
+                    const int s = o & 3;
+                    const int cnt = (s + n) >> 2;
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(valS) + (o >> 2);
+                    const int sh = 32 - 8 * s;             // stream = [headw, W0..W7]; word i starts s bytes before W[i-1]'s end
+                    uint32_t prev = headw;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t w = s ? __funnelshift_r(prev, W[i], sh) : W[i];
+                        if (i < cnt) dst[i] = w;
+                        prev = W[i];
+                    }
+                    if (8 < cnt) dst[8] = __funnelshift_r(prev, 0u, sh);
+                    // the thread that holds the end-of-data terminator flushes the trailing partial word byte by byte
+                    // (bytes before this thread's first character come from the previous thread's tail word)
+                    if (has_term) {
+                        const int end = o + n - 1;               // staging position just after the last real character
+                        for (int q = end & ~3; q < end; ++q) {
+                            const int j = q - o;
+                            const uint32_t src = j >= 0 ? W[j >> 2] >> ((j & 3) * 8) : headw >> ((4 + j) * 8);
+                            if (q >= 0) valS[q] = (uint8_t)(src & 0xFFu);
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < n; ++j) {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int b = 0; b < 5; ++b) v |= ((V[b] >> j) & 1u) << b;
+                        valS[o + j] = (uint8_t)v;
+                    }
+                }
+            }
+        }
         __syncthreads();  // (I)
 
-        auto is_split = [&](int c) -> bool { return (splitS[c >> 5] >> (c & 31)) & 1u; };
+        auto is_split = [&](int c) -> bool {   // c = tile character index; thread-local planes live in splitS
+            // find the thread that holds character c: threads hold at least 8 characters each in valid UTF-8
+            int t = c >> 5;
+            while (t + 1 < NT && cprefS[t + 1] <= c) ++t;
+            return (splitS[t] >> (c - cprefS[t])) & 1u;
+        };
         // feature sums of characters c, c-1, ... down to the token's first character (a split) or c_lo
         auto walk_back = [&](int c, unsigned acc[7], bool &hit) {
             hit = false;
@@ -755,21 +1039,23 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
                 if (is_split(c)) { hit = true; break; }
             }
         };
-        if (want_feats && n_own > 0 && tid == ((c_hi - 1) >> 5)) {
-            unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit;
-            walk_back(c_hi - 1, acc, hit);
-            sc.open_has = hit ? 1u : 0u;
-            for (int g = 0; g < 7; ++g) sc.open_sums[g] = acc[g];
-            sc.open_sums[7] = 0;
+        if (kWords && want_feats) {
+            if (n_own > 0 && tid == END_OWNED_THREAD) {
+                unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit;
+                walk_back(c_hi - 1, acc, hit);
+                sc.open_has = hit ? 1u : 0u;
+                for (int g = 0; g < 7; ++g) sc.open_sums[g] = acc[g];
+                sc.open_sums[7] = 0;
+            }
+            __syncthreads();
         }
-        if (want_feats) __syncthreads();
 
         // ------------------------------------------------------------------ chain 2
         if (warp == 0) {
             Chain2 a;
             a.k = (unsigned long long)ntok_tile; a.reset = 0;
-            a.has_split = want_feats ? sc.open_has : 0u;
-            for (int g = 0; g < 8; ++g) a.sums[g] = (want_feats && n_own > 0) ? sc.open_sums[g] : 0u;
+            a.has_split = (kWords && want_feats) ? sc.open_has : 0u;
+            for (int g = 0; g < 8; ++g) a.sums[g] = (kWords && want_feats && n_own > 0) ? sc.open_sums[g] : 0u;
             if (lane == 0) publish(p.agg2 + tile, p.status2 + tile, a, p.epoch, 1u);
             Chain2 pre = lookback<Chain2>(tile, p.status2, p.agg2, p.inc2, p.epoch, p.result, lane);
             if (lane == 0) {
@@ -780,15 +1066,25 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
                 for (int g = 0; g < 8; ++g) sc.carry_sums[g] = pre.sums[g];
             }
         }
+        // split mask out while warp 0 looks back: 16-byte chunks, byte-wise at the two ragged ends
+        if (want_splits && n_own > 0) {
+            int8_t *dst = p.splits + G_in;                  // dst[j] <-> valS[a16 + j]
+            const int head = (16 - a16) & 15;               // bytes before the first 16-byte boundary
+            const int nh = head < n_own ? head : n_own;
+            if (tid < nh) dst[tid] = (int8_t)valS[a16 + tid];
+            const int nchunks = (n_own - nh) >> 4;
+            const uint4 *src = reinterpret_cast<const uint4 *>(valS + a16 + nh);
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + nh);
+            for (int i = tid; i < nchunks; i += NT) d4[i] = src[i];
+            const int done = nh + (nchunks << 4);
+            if (tid < n_own - done) dst[done + tid] = (int8_t)valS[a16 + done + tid];
+        }
+        if (tid == NT - 1 && ntok_tile >= 1 && ntok_tile <= SPAN_STAGE - 1) spanS[2 * (ntok_tile - 1) + 3] = -1;  // "still open"
         __syncthreads();  // (J)
         const unsigned long long K_in = sc.K_in;
 
         // ------------------------------------------------------------------ phase 4: emission
-        if (want_splits) {
-            int8_t *dst = p.splits + G_in;
-            for (int j = tid; j < n_own; j += NT) dst[j] = (int8_t)valS[c_lo + j];
-        }
-        if (want_matrix) {
+        if (kWords && want_matrix) {
             int8_t *dst = p.matrix + G_in * NFEAT;
             const int nb = n_own * NFEAT;
             for (int j = tid; j < nb; j += NT) {
@@ -796,6 +1092,7 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
                 dst[j] = (int8_t)((wordS[widx(c_lo + c)] >> f) & 1u);
             }
         }
+        const bool stage = want_spans && ntok_tile <= SPAN_STAGE - 1 && K_in + (unsigned long long)ntok_tile <= (unsigned long long)p.cap_tokens;
         if (want_spans || want_feats) {
             // string-relative index of character c: (G_in + c - c_lo) - (global index of its string's first character)
             unsigned long long gbase = lf_excl >= 0 ? G_in + (unsigned long long)(lf_excl - c_lo) : sc.base_in;
@@ -805,16 +1102,17 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
             if (over && tid == 0) atomicOr(&p.result->error, 4u);
             while (ev) {
                 const int i = __ffs(ev) - 1; const uint32_t b = 1u << i; ev &= ev - 1;
-                const int c = cb + i;
+                const int c = c0 + i;
                 const unsigned long long g = G_in + (unsigned long long)(c - c_lo);
                 if (Fm & b) gbase = g;
                 const int idx = (int)(g - gbase);
-                const long long ordx = (long long)K_in + tp + rank;   // tokens counted before this character
+                const int lord = tp + rank;                        // tile-local ordinal of the token counted here
+                const long long ordx = (long long)K_in + lord;     // tokens counted before this character
                 if (EW & b) {  // previous token [.., idx)
                     const long long k = ordx - 1;
                     if (k >= 0 && k < p.cap_tokens) {
-                        if (want_spans) p.spans[2 * k + 1] = idx;
-                        if (want_feats) {
+                        if (want_spans) { if (stage && lord >= 1) spanS[2 * (lord - 1) + 3] = idx; else p.spans[2 * k + 1] = idx; }
+                        if (kWords && want_feats) {
                             unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit;
                             walk_back(c - 1, acc, hit);
                             if (!hit) for (int q = 0; q < 7; ++q) acc[q] = __vadd4(acc[q], sc.carry_sums[q]);
@@ -824,14 +1122,16 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
                     }
                 }
                 if (E & b) {
-                    if (want_spans && ordx < p.cap_tokens) p.spans[2 * ordx] = (SPLIT & b) ? idx : idx - 1;
+                    const int sidx = (SPLIT & b) ? idx : idx - 1;
+                    if (want_spans && ordx < p.cap_tokens) { if (stage) spanS[2 * lord + 2] = sidx; else p.spans[2 * ordx] = sidx; }
                     ++rank;
                 }
                 if (EL & b) {  // last token of the string [.., idx + 1)
-                    const long long k = (long long)K_in + tp + rank - 1;
+                    const int ll = tp + rank - 1;
+                    const long long k = (long long)K_in + ll;
                     if (k >= 0 && k < p.cap_tokens) {
-                        if (want_spans) p.spans[2 * k + 1] = idx + 1;
-                        if (want_feats) {
+                        if (want_spans) { if (stage && ll >= 0) spanS[2 * ll + 3] = idx + 1; else p.spans[2 * k + 1] = idx + 1; }
+                        if (kWords && want_feats) {
                             unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit;
                             walk_back(c, acc, hit);
                             if (!hit) for (int q = 0; q < 7; ++q) acc[q] = __vadd4(acc[q], sc.carry_sums[q]);
@@ -846,29 +1146,65 @@ __global__ void __launch_bounds__(NT, 1) tokenize_kernel(const Params p)
         {
             const long long s_end = p.tile_first_str[tile + 1];
             for (long long s = p.tile_first_str[tile] + tid; s < s_end; s += NT) {
-                const int c = cidx(int(p.offsets[s] - w0));
+                const int wb = int(p.offsets[s] - w0);
+                const int c = cidx(wb);
                 p.char_off[s] = (long long)(G_in + (unsigned long long)(c - c_lo));
-                p.tok_off[s] = (long long)K_in + tokprefS[c >> 5] + __popc(emitS[c >> 5] & mask_lt(c & 31));
+                const int t = wb >> 5;
+                p.tok_off[s] = (long long)K_in + tokprefS[t] + __popc(emitS[t] & mask_lt(c - cprefS[t]));
             }
         }
         if (tile == p.ntiles - 1 && tid == 0) {
             p.result->n_chars = G_in + (unsigned long long)n_own;
             p.result->n_tokens = K_in + (unsigned long long)ntok_tile;
         }
+        if (stage) {
+            // staged spans -> global, 8-byte pairs (the end of the token open at the tile end is written by a later tile;
+            // the end of the token open at the tile start, staged in slot -1, goes to token K_in - 1)
+            __syncthreads();
+            int2 *dst = reinterpret_cast<int2 *>(p.spans) + K_in;
+            const int2 *src = reinterpret_cast<const int2 *>(spanS) + 1;
+            // the last staged token may still be open (its end is written by a later tile): write only its start
+            for (int i = tid; i < ntok_tile; i += NT) {
+                const int2 v = src[i];
+                if (v.y >= 0) dst[i] = v;
+                else p.spans[2 * (K_in + i)] = v.x;
+            }
+        }
     }
+}
+
+template <bool kDefault, bool kWords>
+static cudaError_t launch_one(const Params &p, int grid, cudaStream_t s)
+{
+    const size_t smem = tokenize_smem_bytes(p.tl, kWords);
+    static size_t configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(tokenize_kernel<kDefault, kWords>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    tokenize_kernel<kDefault, kWords><<<grid, NT, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words)
+{
+    int nb = 0;
+    const size_t smem = tokenize_smem_bytes(tl, want_words);
+    cudaError_t e;
+    if (is_default && !want_words) { cudaFuncSetAttribute(tokenize_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<true, false>, NT, smem); }
+    else if (is_default) { cudaFuncSetAttribute(tokenize_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<true, true>, NT, smem); }
+    else if (!want_words) { cudaFuncSetAttribute(tokenize_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<false, false>, NT, smem); }
+    else { cudaFuncSetAttribute(tokenize_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<false, true>, NT, smem); }
+    if (e != cudaSuccess) { cudaGetLastError(); return 1; }
+    return nb < 1 ? 1 : nb;
 }
 
 cudaError_t launch_tokenize(const Params &p, int grid, cudaStream_t s)
 {
-    const size_t smem = tokenize_smem_bytes(p.tl);
-    static size_t configured = 0;
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(tokenize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    tokenize_kernel<<<grid, NT, smem, s>>>(p);
-    return cudaGetLastError();
+    const bool words = (p.what & (4u | 8u)) != 0u;
+    if (p.rules.is_default) return words ? launch_one<true, true>(p, grid, s) : launch_one<true, false>(p, grid, s);
+    return words ? launch_one<false, true>(p, grid, s) : launch_one<false, false>(p, grid, s);
 }
 
 // =====================================================================================================
