@@ -50,6 +50,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     subprocess.run([sys.executable, str(ROOT / "tools" / "gen_tables.py")], check=True,
                    stdout=None if verbose else subprocess.DEVNULL)
     cmd = [find_nvcc(), *NVCC_FLAGS]
+    if os.environ.get("LATOK_PROFILE"):
+        cmd += ["-DLATOK_PROFILE"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [str(s) for s in SOURCES] + ["-o", str(LIB)]

@@ -127,9 +127,9 @@ struct latok_b200_engine {
     DevBuf<long long> d_off, d_first, d_char_off, d_tok_off;
     DevBuf<int8_t> d_splits, d_feats, d_matrix;
     DevBuf<int32_t> d_spans;
-    DevBuf<Chain1> agg1, inc1;
-    DevBuf<Chain2> agg2, inc2;
-    DevBuf<unsigned> st1, st2;
+    DevBuf<AggRec> agg;
+    DevBuf<IncRec> inc;
+    DevBuf<OpenSums> osum;
     DevBuf<Result> d_result;
     PinBuf<uint8_t> h_in;
     PinBuf<long long> h_off;
@@ -267,7 +267,7 @@ int latok_b200_destroy(latok_b200_engine *e)
     e->d_table.release(); e->d_in.release(); e->d_scratch.release(); e->d_scratch2.release(); e->d_scratch3.release();
     e->d_off.release(); e->d_first.release(); e->d_char_off.release(); e->d_tok_off.release();
     e->d_splits.release(); e->d_feats.release(); e->d_matrix.release(); e->d_spans.release();
-    e->agg1.release(); e->inc1.release(); e->agg2.release(); e->inc2.release(); e->st1.release(); e->st2.release();
+    e->agg.release(); e->inc.release(); e->osum.release();
     e->d_result.release();
     e->h_in.release(); e->h_off.release(); e->h_result.release();
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
@@ -309,13 +309,10 @@ static int run_device(latok_b200_engine *e)
 {
     const long long ntiles = e->n_bytes / TILE + 1;
     if (int r = e->d_first.ensure((size_t)ntiles + 1)) return r;
-    if (int r = e->agg1.ensure((size_t)ntiles)) return r;
-    if (int r = e->inc1.ensure((size_t)ntiles)) return r;
-    if (int r = e->agg2.ensure((size_t)ntiles)) return r;
-    if (int r = e->inc2.ensure((size_t)ntiles)) return r;
-    // status words carry the launch epoch, so they are zeroed only when (re)allocated
-    if ((size_t)ntiles > e->st1.cap) { if (int r = e->st1.ensure((size_t)ntiles, true)) return r; }
-    if ((size_t)ntiles > e->st2.cap) { if (int r = e->st2.ensure((size_t)ntiles, true)) return r; }
+    // the status word of every aggregate record carries the launch epoch, so records are zeroed only when (re)allocated
+    if ((size_t)ntiles > e->agg.cap) { if (int r = e->agg.ensure((size_t)ntiles, true)) return r; }
+    if (int r = e->inc.ensure((size_t)ntiles)) return r;
+    if (e->what & LATOK_B200_FEATS) { if (int r = e->osum.ensure((size_t)ntiles)) return r; }
     if (int r = e->d_splits.ensure((size_t)e->n_bytes + 64)) return r;
     if (int r = e->d_char_off.ensure((size_t)e->n_strings + 1)) return r;
     if (int r = e->d_tok_off.ensure((size_t)e->n_strings + 1)) return r;
@@ -325,8 +322,7 @@ static int run_device(latok_b200_engine *e)
 
     e->epoch = (e->epoch + 1) & 0x3FFFFFFFu;
     if (e->epoch == 0) {  // wrapped: clear stale status words
-        CU(cudaMemsetAsync(e->st1.p, 0, e->st1.cap * sizeof(unsigned), e->stream));
-        CU(cudaMemsetAsync(e->st2.p, 0, e->st2.cap * sizeof(unsigned), e->stream));
+        CU(cudaMemsetAsync(e->agg.p, 0, e->agg.cap * sizeof(AggRec), e->stream));
         e->epoch = 1;
     }
     Params p;
@@ -337,8 +333,7 @@ static int run_device(latok_b200_engine *e)
     p.feats = e->d_feats.p; p.matrix = e->d_matrix.p;
     p.cap_tokens = (long long)(e->d_spans.cap / 2);
     p.what = e->what;
-    p.agg1 = e->agg1.p; p.inc1 = e->inc1.p; p.agg2 = e->agg2.p; p.inc2 = e->inc2.p;
-    p.status1 = e->st1.p; p.status2 = e->st2.p; p.epoch = e->epoch;
+    p.agg = e->agg.p; p.inc = e->inc.p; p.osum = e->osum.p; p.epoch = e->epoch;
     p.ticket = &e->d_result.p->ticket; p.ticket_base = 0;
     p.result = e->d_result.p;
     p.table_blob = e->d_table.p; p.tl = e->tl; p.rules = e->rules;
@@ -437,6 +432,11 @@ int latok_b200_sizes(latok_b200_engine *e, int64_t *n_chars, int64_t *n_tokens)
             if (int r = run_device(e)) return r;
             continue;
         }
+        if (getenv("LATOK_B200_PRINT_PROF")) {
+            fprintf(stderr, "[latok prof]");
+            for (int i = 0; i < 16; ++i) fprintf(stderr, " %llu", res.prof[i]);
+            fprintf(stderr, "\n");
+        }
         e->n_chars = (long long)res.n_chars; e->n_tokens = (long long)res.n_tokens; e->walks = (long long)res.walks;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e->ev_k0, e->ev_k1) == cudaSuccess) e->last_kernel_ms = ms; else cudaGetLastError();
@@ -518,6 +518,19 @@ int latok_b200_last_stats(latok_b200_engine *e, float *tokenize_kernel_ms, int64
     if (tokenize_kernel_ms) *tokenize_kernel_ms = e->last_kernel_ms;
     if (lookahead_walks) *lookahead_walks = e->walks;
     return LATOK_B200_OK;
+}
+
+/* debugging aid (not part of the public header): copy the per-tile inclusive prefixes of the last run */
+extern "C" __attribute__((visibility("default"))) int latok_b200_debug_chain(latok_b200_engine *e, void *inc_out, void *agg_out, int64_t max_tiles)
+{
+    if (!e) return 1;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    const int64_t nt = e->n_bytes / TILE + 1;
+    const int64_t n = nt < max_tiles ? nt : max_tiles;
+    cudaMemcpy(inc_out, e->inc.p, sizeof(IncRec) * n, cudaMemcpyDeviceToHost);
+    cudaMemcpy(agg_out, e->agg.p, sizeof(AggRec) * n, cudaMemcpyDeviceToHost);
+    return (int)n;
 }
 
 int latok_b200_host_alloc(void **ptr, size_t bytes)

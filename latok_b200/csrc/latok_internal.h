@@ -49,28 +49,33 @@ struct RuleSet {
     uint32_t sym[MAX_RULE_ROWS + 1];
 };
 
-// ---- decoupled look-back state ----------------------------------------------------------------
-// chain 1: character count, start of the current string, whitespace-chunk backlog function
-struct __align__(16) Chain1 {
-    unsigned long long n;    // aggregate: characters in tile | prefix: characters before the boundary
-    unsigned long long lf;   // aggregate: tile-relative index of the last string start | prefix: its global index
-    int u, v;                // backlog transfer function x -> max(x + u, v)   | prefix: (NEG, x)
-    unsigned has;            // aggregate: tile contains a string start
-    unsigned reset;          // used in registers only
+// ---- decoupled look-back state (ONE chain) ----------------------------------------------------
+// Every tile publishes a 16-byte aggregate as soon as it has finished computing (state 1), computed
+// under the assumption that no block-mask backlog enters the tile (true for almost every tile), and
+// later its inclusive prefix (state 2).  A reader reconstructs the backlog entering each aggregate it
+// consumes; if that is non-zero it waits for that tile's inclusive prefix instead.
+struct __align__(16) AggRec {
+    unsigned status;   // (epoch << 2) | state
+    unsigned n_lf;     // characters in the tile | (tile-relative index of the last string start + 1) << 16
+    unsigned ntok_v;   // tokens counted in the tile (backlog-in = 0) | backlog-out for backlog-in = 0 << 16
+    int u;             // backlog transfer function x -> max(x + u, v); NEG if the tile holds a string start
 };
-// chain 2: emitted-token count and the feature sums of the token still open at the boundary
-struct __align__(16) Chain2 {
-    unsigned long long k;
-    unsigned has_split;
-    unsigned reset;
-    unsigned sums[8];        // 25 byte counters packed 4 per word (7 words used)
+struct __align__(16) IncRec {
+    unsigned long long G;     // characters before the end of the tile
+    unsigned long long base;  // global index of the first character of the string open at the end of the tile
+    unsigned long long K;     // tokens counted before the end of the tile
+    int x;                    // backlog leaving the tile
+    int pad;
 };
+// token-feature mode only: feature sums of the token still open at the end of a tile
+struct __align__(16) OpenSums { unsigned has_split; unsigned pad[3]; unsigned sums[8]; };
 
 struct Result {
     unsigned long long n_chars;
     unsigned long long n_tokens;
     unsigned long long walks;
     unsigned long long ticket;   // dynamic tile counter (zeroed with the rest of the struct before each launch)
+    unsigned long long prof[16]; // LATOK_PROFILE builds: summed clock64() deltas per phase (thread 0 of every CTA)
     unsigned int error;      // bit 0: watchdog, bit 1: offsets not monotone, bit 2: token capacity exceeded
     unsigned int abort_flag;
 };
@@ -90,9 +95,9 @@ struct Params {
     int8_t *matrix;
     long long cap_tokens;
     uint32_t what;
-    Chain1 *agg1, *inc1;
-    Chain2 *agg2, *inc2;
-    unsigned *status1, *status2;
+    AggRec *agg;
+    IncRec *inc;
+    OpenSums *osum;
     unsigned epoch;
     unsigned long long *ticket;
     unsigned long long ticket_base;

@@ -47,6 +47,12 @@ __device__ __forceinline__ Fn fn_compose(Fn f, Fn g)  // g after f
 }
 __device__ __forceinline__ int fn_apply(Fn f, int x) { return max(x + f.u, f.v); }
 
+#ifdef LATOK_PROFILE
+#define PROF(i) do { if (threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&p.result->prof[i], (unsigned long long)(_t - _prof_t)); _prof_t = _t; } } while (0)
+#else
+#define PROF(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(void *bar, int count)
@@ -173,144 +179,6 @@ __device__ __forceinline__ void eval_rules(const RuleSet &c_rules, uint32_t w, u
 // 4 feature bits -> 4 byte counters (bit k -> byte k)
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
-// ---- chain combine operators (older `a`, newer `b`; a reset element discards everything older) ----
-__device__ __forceinline__ Chain1 combine1(const Chain1 &a, const Chain1 &b)
-{
-    if (b.reset) return b;
-    Chain1 r;
-    r.reset = a.reset;
-    r.n = a.n + b.n;
-    r.has = a.has | b.has;
-    r.lf = b.has ? a.n + b.lf : a.lf;
-    Fn f = fn_compose(Fn{a.u, a.v}, Fn{b.u, b.v});
-    r.u = f.u; r.v = f.v;
-    return r;
-}
-__device__ __forceinline__ Chain2 combine2(const Chain2 &a, const Chain2 &b)
-{
-    if (b.reset) return b;
-    Chain2 r;
-    r.reset = a.reset;
-    r.k = a.k + b.k;
-    r.has_split = a.has_split | b.has_split;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r.sums[i] = b.has_split ? b.sums[i] : __vadd4(a.sums[i], b.sums[i]);
-    return r;
-}
-__device__ __forceinline__ Chain1 shfl_up_c(const Chain1 &e, int d)
-{
-    Chain1 o;
-    o.n = __shfl_up_sync(0xFFFFFFFFu, e.n, d); o.lf = __shfl_up_sync(0xFFFFFFFFu, e.lf, d);
-    o.u = __shfl_up_sync(0xFFFFFFFFu, e.u, d); o.v = __shfl_up_sync(0xFFFFFFFFu, e.v, d);
-    o.has = __shfl_up_sync(0xFFFFFFFFu, e.has, d); o.reset = __shfl_up_sync(0xFFFFFFFFu, e.reset, d);
-    return o;
-}
-__device__ __forceinline__ Chain2 shfl_up_c(const Chain2 &e, int d)
-{
-    Chain2 o;
-    o.k = __shfl_up_sync(0xFFFFFFFFu, e.k, d);
-    o.has_split = __shfl_up_sync(0xFFFFFFFFu, e.has_split, d); o.reset = __shfl_up_sync(0xFFFFFFFFu, e.reset, d);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o.sums[i] = __shfl_up_sync(0xFFFFFFFFu, e.sums[i], d);
-    return o;
-}
-__device__ __forceinline__ Chain1 shfl_c(const Chain1 &e, int src)
-{
-    Chain1 o;
-    o.n = __shfl_sync(0xFFFFFFFFu, e.n, src); o.lf = __shfl_sync(0xFFFFFFFFu, e.lf, src);
-    o.u = __shfl_sync(0xFFFFFFFFu, e.u, src); o.v = __shfl_sync(0xFFFFFFFFu, e.v, src);
-    o.has = __shfl_sync(0xFFFFFFFFu, e.has, src); o.reset = __shfl_sync(0xFFFFFFFFu, e.reset, src);
-    return o;
-}
-__device__ __forceinline__ Chain2 shfl_c(const Chain2 &e, int src)
-{
-    Chain2 o;
-    o.k = __shfl_sync(0xFFFFFFFFu, e.k, src);
-    o.has_split = __shfl_sync(0xFFFFFFFFu, e.has_split, src); o.reset = __shfl_sync(0xFFFFFFFFu, e.reset, src);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o.sums[i] = __shfl_sync(0xFFFFFFFFu, e.sums[i], src);
-    return o;
-}
-__device__ __forceinline__ Chain1 origin1() { Chain1 o; o.n = 0; o.lf = 0; o.u = NEG; o.v = 0; o.has = 1; o.reset = 1; return o; }
-__device__ __forceinline__ Chain2 origin2() { Chain2 o; o.k = 0; o.has_split = 1; o.reset = 1; for (int i = 0; i < 8; ++i) o.sums[i] = 0; return o; }
-__device__ __forceinline__ Chain1 combine_c(const Chain1 &a, const Chain1 &b) { return combine1(a, b); }
-__device__ __forceinline__ Chain2 combine_c(const Chain2 &a, const Chain2 &b) { return combine2(a, b); }
-__device__ __forceinline__ void origin_c(Chain1 &o) { o = origin1(); }
-__device__ __forceinline__ void origin_c(Chain2 &o) { o = origin2(); }
-
-template <class T>
-__device__ __forceinline__ T load_state(const T *p)
-{
-    // 16-byte L2 loads (never the non-coherent L1 path)
-    T r;
-    const int4 *s = reinterpret_cast<const int4 *>(p);
-    int4 *d = reinterpret_cast<int4 *>(&r);
-#pragma unroll
-    for (int i = 0; i < int(sizeof(T) / 16); ++i) d[i] = __ldcg(s + i);
-    return r;
-}
-template <class T>
-__device__ __forceinline__ void store_state(T *p, const T &v)
-{
-    const int4 *s = reinterpret_cast<const int4 *>(&v);
-    int4 *d = reinterpret_cast<int4 *>(p);
-#pragma unroll
-    for (int i = 0; i < int(sizeof(T) / 16); ++i) __stcg(d + i, s[i]);
-}
-
-// Publish this tile's aggregate (state 1) or inclusive prefix (state 2).  Called by one lane.
-template <class T>
-__device__ __forceinline__ void publish(T *slot, unsigned *status, const T &v, unsigned epoch, unsigned state)
-{
-    store_state(slot, v);
-    __threadfence();
-    st_volatile_u32(status, (epoch << 2) | state);
-}
-
-// Decoupled look-back over the preceding tiles, 32 at a time (warp 0 only).  Returns the
-// exclusive prefix of `tile` as a reset element in every lane.
-template <class T>
-__device__ T lookback(long long tile, const unsigned *status, const T *agg, const T *inc, unsigned epoch,
-                      Result *result, int lane)
-{
-    T acc;
-    bool have = false;
-    for (long long base = tile - 1;; base -= 32) {
-        long long idx = base - (31 - lane);  // lane 31 looks at the nearest predecessor
-        T e;
-        if (idx < 0) {
-            origin_c(e);
-        } else {
-            unsigned s, spins = 0;
-            for (;;) {
-                s = ld_volatile_u32(status + idx);
-                if ((s >> 2) == epoch && (s & 3u) != 0u) break;
-                if (++spins > SPIN_LIMIT || (((spins & 1023u) == 0u) && ld_volatile_u32(&result->abort_flag))) {
-                    atomicOr(&result->error, 1u);
-                    st_volatile_u32(&result->abort_flag, 1u);
-                    s = 2u;  // give up: behave as if an (arbitrary) prefix was found so the kernel terminates
-                    break;
-                }
-                __nanosleep(20);
-            }
-            __threadfence();
-            const bool is_inc = (s & 3u) == 2u;
-            e = load_state(is_inc ? inc + idx : agg + idx);
-            e.reset = is_inc ? 1u : 0u;
-        }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            T o = shfl_up_c(e, d);
-            if (lane >= d) e = combine_c(o, e);
-        }
-        T win = shfl_c(e, 31);
-        acc = have ? combine_c(win, acc) : win;
-        have = true;
-        if (acc.reset) break;
-    }
-    return acc;
-}
-
 // ---- look-ahead walk (rare): the whitespace chunk open at the end of a tile did not close inside
 // the right halo.  Warp 0 scans forward from global byte `pos0` until the chunk closes (a SPACE
 // character or the end of the string) and reports whether a mark occurs up to and including the
@@ -369,18 +237,162 @@ __device__ bool walk_ahead(const Params &p, const Tables &t, long long pos0, int
 }
 
 // =====================================================================================================
-// tokenize_kernel (v2, bit-plane formulation)
-//
-// Every thread owns 32 window bytes and keeps its characters as 32-bit BIT-PLANES in registers: bit j of
-// plane f = feature f of the thread's j-th character.  All per-character logic of the reference
-// (context features, the three combo-matrix rules, the block mask, split values, token flags) then runs
-// 32 characters per instruction.
+// Decoupled look-back (single chain, 16-byte aggregate records, LB_WINDOW predecessors per step)
+// =====================================================================================================
+constexpr int LB_PER_LANE = 8;
+constexpr int LB_WINDOW = 32 * LB_PER_LANE;
+
+__device__ __forceinline__ uint4 ld_rec(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_rec(void *p, uint4 v)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct Prefix { unsigned long long G, base, K; int x; };
+
+// spin until tile `idx` has published at least `min_state` for this launch; returns the record
+__device__ __forceinline__ uint4 wait_rec(const AggRec *agg, long long idx, unsigned epoch, unsigned min_state, Result *result, bool &ok)
+{
+    uint4 r;
+    unsigned spins = 0;
+    for (;;) {
+        r = ld_rec(agg + idx);
+        if ((r.x >> 2) == epoch && (r.x & 3u) >= min_state) break;
+        if (++spins > SPIN_LIMIT || (((spins & 1023u) == 0u) && ld_volatile_u32(&result->abort_flag))) {
+            atomicOr(&result->error, 1u);
+            st_volatile_u32(&result->abort_flag, 1u);
+            ok = false;
+            break;
+        }
+    }
+    return r;
+}
+
+// Exclusive prefix of `tile` (warp 0, all lanes).  Walks back LB_WINDOW tiles at a time until it meets an
+// inclusive prefix.  An aggregate is only valid for a tile that no block-mask backlog enters, i.e. when the
+// inclusive prefix it is chained to carries no backlog and every aggregate between them leaves none
+// (backlog-out for backlog-in 0 is stored in the record).  If that does not hold (rare: a whitespace chunk
+// with several marks, or a chunk longer than the halo) the walk waits for the inclusive prefix of the tile
+// right after the offending one -- that tile recomputes with its real backlog -- and starts over.
+__device__ Prefix lookback(long long tile, const Params &p, int lane)
+{
+    Prefix out;
+    out.G = 0; out.base = 0; out.K = 0; out.x = 0;
+    if (tile == 0) return out;
+    for (int restart = 0;; ++restart) {
+        unsigned long long sum_n = 0, sum_k = 0;     // characters / tokens of the consumed aggregates
+        unsigned long long lf_part = 0; bool lf_found = false;
+        long long viol = -1;                         // newest tile whose successor's aggregate must not be used
+        int x_in = 0; bool x_set = false;
+        bool ok = true, done = false;
+        for (long long newest = tile - 1; !done; newest -= LB_WINDOW) {
+            // lane l covers tiles first .. first + LB_PER_LANE - 1 (older lanes = older tiles)
+            const long long first = newest - (long long)(31 - lane) * LB_PER_LANE - (LB_PER_LANE - 1);
+            int rj = -1;                              // newest inclusive element of this lane
+            unsigned long long rG = 0, rB = 0, rK = 0; int rx = 0;
+            unsigned ln = 0, lk = 0, llf = 0; bool lhas = false; long long lviol = -1; int lastv = 0;
+            // all records of this lane in flight at once; re-poll only the ones not yet published
+            uint4 rec[LB_PER_LANE];
+#pragma unroll
+            for (int j = 0; j < LB_PER_LANE; ++j) { rec[j] = make_uint4(0, 0, 0, 0); if (first + j >= 0) rec[j] = ld_rec(p.agg + (first + j)); }
+            {
+                unsigned spins = 0;
+                for (;;) {
+                    bool pending = false;
+#pragma unroll
+                    for (int j = 0; j < LB_PER_LANE; ++j)
+                        if (first + j >= 0 && !((rec[j].x >> 2) == p.epoch && (rec[j].x & 3u) != 0u)) { rec[j] = ld_rec(p.agg + (first + j)); pending = true; }
+                    if (!pending) break;
+                    if (++spins > SPIN_LIMIT || (((spins & 1023u) == 0u) && ld_volatile_u32(&p.result->abort_flag))) {
+                        atomicOr(&p.result->error, 1u);
+                        st_volatile_u32(&p.result->abort_flag, 1u);
+                        ok = false;
+                        break;
+                    }
+                }
+            }
+            // the newest inclusive record of this lane: fetch its prefix
+#pragma unroll
+            for (int j = 0; j < LB_PER_LANE; ++j) if (first + j >= 0 && (rec[j].x & 3u) == 2u) rj = j;
+            if (rj >= 0) {
+                __threadfence();
+                const IncRec *ir = p.inc + (first + rj);
+                const uint4 a = ld_rec(ir), b = ld_rec(reinterpret_cast<const uint4 *>(ir) + 1);
+                rG = a.x | ((unsigned long long)a.y << 32); rB = a.z | ((unsigned long long)a.w << 32);
+                rK = b.x | ((unsigned long long)b.y << 32); rx = (int)b.z;
+            }
+#pragma unroll
+            for (int j = 0; j < LB_PER_LANE; ++j) {
+                const long long idx = first + j;
+                if (idx < -1) continue;
+                if (idx == -1) { if (rj < 0) { rj = j; rG = rB = rK = 0; rx = 0; } continue; }
+                if (j <= rj) continue;                          // superseded by (or is) the inclusive record
+                const uint4 r = rec[j];
+                const unsigned n = r.y & 0xFFFFu, lf1 = r.y >> 16, k = r.z & 0xFFFFu; const int v = (int)(r.z >> 16);
+                if (lf1) { llf = ln + (lf1 - 1u); lhas = true; }
+                ln += n; lk += k;
+                if (v != 0 && idx != tile - 1) lviol = idx;      // its successor needs a real backlog
+                if (idx == tile - 1) lastv = v;
+            }
+            const unsigned has_reset = __ballot_sync(0xFFFFFFFFu, rj >= 0);
+            const int Lr = has_reset ? 31 - __clz(has_reset) : -1;
+            const bool contrib = lane >= Lr;          // lanes older than the newest inclusive element are superseded
+            // characters / tokens
+            const unsigned wn = __reduce_add_sync(0xFFFFFFFFu, contrib ? ln : 0u), wk = __reduce_add_sync(0xFFFFFFFFu, contrib ? lk : 0u);
+            // newest string start among the consumed aggregates of this window
+            const unsigned hasm = __ballot_sync(0xFFFFFFFFu, contrib && lhas);
+            if (!lf_found && hasm) {
+                const int H = 31 - __clz(hasm);
+                const unsigned older = __reduce_add_sync(0xFFFFFFFFu, (contrib && lane < H) ? ln : 0u);
+                lf_part = (unsigned long long)older + __shfl_sync(0xFFFFFFFFu, llf, H);
+                lf_found = true;
+            } else if (lf_found) lf_part += wn;       // this whole window lies before the string start found earlier
+            sum_n += wn; sum_k += wk;
+            // newest offending tile of this window (64-bit max through two 32-bit reductions on the offset from `newest`)
+            const int voff = (contrib && lviol >= 0) ? (int)(newest - lviol) : 0x7FFFFFFF;   // smaller offset = newer
+            const int vmin = __reduce_min_sync(0xFFFFFFFFu, voff);
+            if (vmin != 0x7FFFFFFF && viol < 0) viol = newest - vmin;
+            if (!x_set) { x_in = __shfl_sync(0xFFFFFFFFu, lastv, 31); x_set = true; }
+            if (!__all_sync(0xFFFFFFFFu, ok)) { out.x = 0; return out; }    // watchdog tripped: error flag is set
+            if (Lr >= 0) {
+                const unsigned long long G0 = __shfl_sync(0xFFFFFFFFu, rG, Lr), B0 = __shfl_sync(0xFFFFFFFFu, rB, Lr);
+                const unsigned long long K0 = __shfl_sync(0xFFFFFFFFu, rK, Lr);
+                const int x0 = __shfl_sync(0xFFFFFFFFu, rx, Lr);
+                const bool consumed_any = sum_n != 0 || sum_k != 0 || __shfl_sync(0xFFFFFFFFu, rj, Lr) != LB_PER_LANE - 1 || Lr != 31 || newest != tile - 1;
+                if (x0 != 0 && consumed_any && viol < 0) {
+                    // the inclusive prefix carries a backlog into the first consumed aggregate
+                    const long long ridx = newest - (long long)(31 - Lr) * LB_PER_LANE - (LB_PER_LANE - 1) + __shfl_sync(0xFFFFFFFFu, rj, Lr);
+                    viol = ridx;
+                }
+                out.G = G0 + sum_n; out.K = K0 + sum_k; out.base = lf_found ? G0 + lf_part : B0;
+                out.x = consumed_any ? x_in : x0;
+                done = true;
+            }
+        }
+        if (viol < 0) return out;
+        // wait for the tile after the offending one to publish its exact inclusive prefix, then walk again
+        bool ok2 = true;
+        wait_rec(p.agg, viol + 1, p.epoch, 2u, p.result, ok2);
+        if (lane == 0) atomicAdd(&p.result->prof[15], 1ull);
+        if (!ok2) return out;
+    }
+}
+
+// =====================================================================================================
+// tokenize_kernel (v3): bit-planes in registers, one speculative look-back chain, chunk-aligned tiles
 // =====================================================================================================
 enum { PL_A = 0, PL_N = 1, PL_NUM = 2, PL_LO = 3, PL_UP = 4, PL_SP = 5, PL_SY = 6, PL_TW = 7, PL_AT = 8, PL_CO = 9,
        PL_SL = 10, PL_PE = 11 };
+constexpr int VPAD = 256;      // staging slack in front of the first owned character
+constexpr int SEARCH = RHALO - TRUST_MARGIN;   // bytes after a nominal tile boundary searched for a closer
 
 struct SmemPlan {
-    int mbar, scal, tile, table, spans, startbits, leadmask, cpref, emit, tokpref, split, edge, scratch, words, total;
+    int mbar, scal, tile0, tile1, table, spans, startbits, leadmask, cpref, emit, tokpref, split, edge, scratch, words, total;
 };
 __host__ __device__ inline SmemPlan smem_plan(int table_bytes, bool want_words)
 {
@@ -388,10 +400,11 @@ __host__ __device__ inline SmemPlan smem_plan(int table_bytes, bool want_words)
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     s.mbar = take(16);
     s.scal = take(256);
-    s.tile = take(WINB + 64);          // window bytes; re-used as the split-value staging buffer
+    s.tile0 = take(WINB + VPAD + 64);   // window bytes; re-used as the split-value staging buffer
+    s.tile1 = take(WINB + VPAD + 64);
     s.table = take(table_bytes);
-    s.spans = take(SPAN_STAGE * 8);
-    s.startbits = take(NT * 4);
+    s.spans = take(SPAN_STAGE * 8 + 16);
+    s.startbits = take(2 * NT * 4);
     s.leadmask = take(NT * 4);
     s.cpref = take((NT + 1) * 4);
     s.emit = take(NT * 4);
@@ -406,56 +419,17 @@ __host__ __device__ inline SmemPlan smem_plan(int table_bytes, bool want_words)
 size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words) { return (size_t)smem_plan(tl.total, want_words).total; }
 
 struct Scalars {          // block-shared scalars
-    long long tile;
+    long long tile_q[2];
+    int tma_used[2];
     unsigned long long G_in, base_in, K_in;
-    int x_in, x_end;
-    int agg_u, agg_v;
-    int need_walk, far, slow_vals;
-    int lf_tile;
+    int x_in;
+    int c_lo, c_hi, lo_found, hi_found;
+    int need_walk, far;
+    int v_tile, x_end;
     unsigned open_has;
     unsigned open_sums[8];
     unsigned carry_sums[8];
 };
-
-__device__ __forceinline__ int block_excl_sum(int v, int *scratch, int &total, int lane, int warp)
-{
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += t; }
-    if (lane == 31) scratch[warp] = inc;
-    __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) { int t = scratch[w]; if (w < warp) base += t; tot += t; }
-    __syncthreads();
-    total = tot;
-    return base + inc - v;
-}
-
-// exclusive scan of backlog functions (composition)
-__device__ __forceinline__ void block_excl_fn(Fn f, int *scratch, Fn &excl, Fn &total, int lane, int warp)
-{
-    Fn inc = f;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int ou = __shfl_up_sync(0xFFFFFFFFu, inc.u, d), ov = __shfl_up_sync(0xFFFFFFFFu, inc.v, d);
-        if (lane >= d) inc = fn_compose(Fn{ou, ov}, inc);
-    }
-    int eu = __shfl_up_sync(0xFFFFFFFFu, inc.u, 1), ev = __shfl_up_sync(0xFFFFFFFFu, inc.v, 1);
-    Fn wex = lane ? Fn{eu, ev} : fn_id();
-    if (lane == 31) { scratch[2 * warp] = inc.u; scratch[2 * warp + 1] = inc.v; }
-    __syncthreads();
-    Fn base = fn_id(), tot = fn_id();
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) {
-        Fn t = Fn{scratch[2 * w], scratch[2 * w + 1]};
-        if (w < warp) base = fn_compose(base, t);
-        tot = fn_compose(tot, t);
-    }
-    __syncthreads();
-    excl = fn_compose(base, wex);
-    total = tot;
-}
 
 // LUT entry (256 + class) of the multi-byte character whose lead byte is p[0] >= 0xC0
 __device__ __forceinline__ uint32_t mb_entry(const uint8_t *p, const Tables &t, uint32_t high_class)
@@ -488,7 +462,7 @@ __device__ __forceinline__ void planes4(const uint32_t a[4], uint32_t &p0, uint3
 __device__ __forceinline__ void transpose32(uint32_t a[32])
 {
 #pragma unroll
-    for (int j = 16, sh = 0; j != 0; j >>= 1, ++sh) {
+    for (int j = 16; j != 0; j >>= 1) {
         const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
@@ -501,18 +475,52 @@ __device__ __forceinline__ void transpose32(uint32_t a[32])
     }
 }
 
+// Backlog through one thread's characters (latok.c:218-244 in scan form): x += 1 at a mark, x = 0 at a
+// string start, a closer (space / end of string) is "hot" if x >= 1 when it is reached, a space then takes
+// one off and the end of a string clears it.  Driven by the (rare) marks; closers are only visited while x > 0.
+__device__ __forceinline__ int eval_backlog(int x, uint32_t Mm, uint32_t FmA, uint32_t S, uint32_t Lm, uint32_t &HOT)
+{
+    HOT = 0;
+    const uint32_t CL = S | Lm;
+    uint32_t remP = 0xFFFFFFFFu, remC = 0xFFFFFFFFu;   // positions still ahead for raising events / closers
+    for (;;) {
+        if (x == 0) {
+            const uint32_t m = Mm & remP;
+            if (!m) break;
+            const uint32_t b = m & (0u - m);
+            x = 1;
+            remC = ~(b - 1u);               // closers at or after the mark
+            remP = remC & ~b;               // events strictly after it
+        } else {
+            const uint32_t pe = (Mm | FmA) & remP, ce = CL & remC;
+            const uint32_t bp = pe & (0u - pe), bc = ce & (0u - ce);
+            if (!bp && !bc) break;
+            if (bp && (!bc || bp <= bc)) {
+                if (FmA & bp) x = 0;
+                if (Mm & bp) ++x;
+                remC = ~(bp - 1u);
+                remP = remC & ~bp;
+            } else {
+                HOT |= bc;
+                if (S & bc) --x;
+                if (Lm & bc) x = 0;            // nothing is carried past the end of a string (the next start resets it anyway)
+                remC = ~(bc - 1u) & ~bc;
+            }
+        }
+    }
+    return x;
+}
+
 template <bool kDefault, bool kWords>
-__global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
+__global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const SmemPlan sp = smem_plan(p.tl.total, kWords);
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.mbar);
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.mbar);   // [2]
     Scalars &sc = *reinterpret_cast<Scalars *>(smem + sp.scal);
-    uint8_t *tileS = smem + sp.tile;
-    uint8_t *valS = smem + sp.tile;      // aliases the window bytes (dead after phase 1)
     uint8_t *tableS = smem + sp.table;
-    int32_t *spanS = reinterpret_cast<int32_t *>(smem + sp.spans);
-    uint32_t *startbits = reinterpret_cast<uint32_t *>(smem + sp.startbits);
+    int2 *spanS = reinterpret_cast<int2 *>(smem + sp.spans);
+    uint32_t *startbitsS = reinterpret_cast<uint32_t *>(smem + sp.startbits);   // [2][NT]
     uint32_t *leadmaskS = reinterpret_cast<uint32_t *>(smem + sp.leadmask);
     int *cprefS = reinterpret_cast<int *>(smem + sp.cpref);
     uint32_t *emitS = reinterpret_cast<uint32_t *>(smem + sp.emit);
@@ -527,10 +535,11 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
 
     if (ld_volatile_u32(&p.result->error) & 2u) return;  // offsets failed validation in tile_index_kernel
 
-    // one-time per CTA: tables into shared memory, mbarrier init
+    // one-time per CTA: tables into shared memory, mbarrier init, clean start-bit maps
     for (int i = tid; i < p.tl.total / 16; i += NT)
         reinterpret_cast<uint4 *>(tableS)[i] = __ldg(reinterpret_cast<const uint4 *>(p.table_blob) + i);
-    if (tid == 0) mbar_init(mbar, 1);
+    startbitsS[tid] = 0; startbitsS[NT + tid] = 0;
+    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); sc.tile_q[0] = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base); }
     __syncthreads();
     Tables tb;
     tb.ascii_feat = reinterpret_cast<const uint16_t *>(tableS + p.tl.ascii_feat);
@@ -542,57 +551,73 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
     const uint32_t *lut1 = lut0 + LUT_ENTRIES, *lut2 = lut1 + LUT_ENTRIES;
     const uint32_t *lutv = reinterpret_cast<const uint32_t *>(tableS + p.tl.lutv);
 
-    uint32_t phase = 0;
+#ifdef LATOK_PROFILE
+    long long _prof_t = clock64();
+#endif
+    uint32_t phase_bits = 0;   // mbarrier phase per buffer
     const bool want_feats = (p.what & 4u) != 0u, want_matrix = (p.what & 8u) != 0u;
     const bool want_spans = (p.what & 2u) != 0u, want_splits = (p.what & 1u) != 0u;
 
-    for (;;) {
-        if (tid == 0) sc.tile = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base);
-        __syncthreads();  // (A) also fences shared-memory reuse across tiles
-        const long long tile = sc.tile;
-        if (tile >= p.ntiles) break;
-
-        // ------------------------------------------------------------------ load window (TMA bulk copy)
-        const long long w0 = tile * (long long)TILE - LHALO;
+    // Start loading window `t` into buffer `b`: TMA bulk copy of the 16-byte aligned interior, plain loads for
+    // the ragged ends, and the string-start bitmap.  Called by all threads.
+    auto begin_load = [&](long long t, int b) {
+        uint8_t *tileS = smem + (b ? sp.tile1 : sp.tile0);
+        const long long w0 = t * (long long)TILE - LHALO;
         const long long lo = w0 < 0 ? 0 : w0;
         long long hi = w0 + WINB;
         const long long full16 = p.n_bytes & ~15LL;
         if (hi > full16) hi = full16;
         const int tma_bytes = hi > lo ? int(hi - lo) : 0;
-        if (tid == 0 && tma_bytes > 0) {
-            fence_proxy_async();
-            mbar_expect_tx(mbar, (uint32_t)tma_bytes);
-            tma_load_1d(tileS + (lo - w0), p.in + lo, (uint32_t)tma_bytes, mbar);
-        }
-        {
-            const int a_end = int(lo - w0);
-            const int b_beg = a_end + tma_bytes;
-            for (int i = tid; i < a_end; i += NT) tileS[i] = 0;
-            for (int i = b_beg + tid; i < WINB + 16; i += NT) {
-                long long g = w0 + i;
-                tileS[i] = (g >= 0 && g < p.n_bytes) ? p.in[g] : (uint8_t)0;
+        if (tid == 0) {
+            sc.tma_used[b] = tma_bytes > 0;
+            if (tma_bytes > 0) {
+                fence_proxy_async();
+                mbar_expect_tx(mbar + b, (uint32_t)tma_bytes);
+                tma_load_1d(tileS + (lo - w0), p.in + lo, (uint32_t)tma_bytes, mbar + b);
             }
         }
-        startbits[tid] = 0;
-        if (tid == 0) { sc.need_walk = 0; sc.far = 0; sc.open_has = 0; sc.slow_vals = 0; }
-        __syncthreads();  // (B)
-        {
-            const long long wend = w0 + WINB;
-            for (long long s = p.tile_first_str[tile] + tid; s <= p.n_strings; s += NT) {
-                long long o = p.offsets[s];
-                if (o >= wend) break;
-                int wb = int(o - w0);
-                atomicOr(&startbits[wb >> 5], 1u << (wb & 31));
-            }
+        const int a_end = int(lo - w0);
+        const int b_beg = a_end + tma_bytes;
+        for (int i = tid; i < a_end; i += NT) tileS[i] = 0;
+        for (int i = b_beg + tid; i < WINB + 16; i += NT) {
+            const long long g = w0 + i;
+            tileS[i] = (g >= 0 && g < p.n_bytes) ? p.in[g] : (uint8_t)0;
         }
-        if (tma_bytes > 0) { mbar_wait(mbar, phase); phase ^= 1u; }
-        __syncthreads();  // (C)
+        uint32_t *sbm = startbitsS + b * NT;
+        const long long wend = w0 + WINB;
+        for (long long s = p.tile_first_str[t] + tid; s <= p.n_strings; s += NT) {
+            const long long o = p.offsets[s];
+            if (o >= wend) break;
+            const int wb = int(o - w0);
+            atomicOr(&sbm[wb >> 5], 1u << (wb & 31));
+        }
+    };
+    if (sc.tile_q[0] < p.ntiles) begin_load(sc.tile_q[0], 0);
+
+    for (int it = 0;; ++it) {
+        const int cur = it & 1;
+        PROF(9);
+        if (tid == 0) sc.tile_q[cur ^ 1] = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base);
+        __syncthreads();  // (A) previous tile completely done; loads/bitmap of this tile issued before are visible
+        const long long tile = sc.tile_q[cur];
+        if (tile >= p.ntiles) break;
+        const long long next_tile = sc.tile_q[cur ^ 1];
+        if (next_tile < p.ntiles) begin_load(next_tile, cur ^ 1);    // prefetch
+        if (sc.tma_used[cur]) { mbar_wait(mbar + cur, (phase_bits >> cur) & 1u); phase_bits ^= 1u << cur; }
+        PROF(0);
+
+        uint8_t *tileS = smem + (cur ? sp.tile1 : sp.tile0);
+        uint8_t *valS = tileS;            // the window bytes are dead after phase 1
+        uint32_t *sbm = startbitsS + cur * NT;
+        const long long w0 = tile * (long long)TILE - LHALO;
+        if (tid == 0) { sc.need_walk = 0; sc.far = 0; sc.open_has = 0; sc.lo_found = 0; sc.hi_found = 0; }
 
         // ------------------------------------------------------------------ phase 1: bytes -> bit-planes
         const int wb0 = tid * 32;
-        const uint32_t sb = startbits[tid];
-        uint32_t lead, mbl;          // lead bytes / lead bytes of multi-byte characters (byte positions)
-        int vhi;                     // number of valid bytes at the low end of this thread's range
+        const uint32_t sb = sbm[tid];
+        sbm[tid] = 0;                       // leave the bitmap clean for the tile after next
+        uint32_t lead, mbl;                 // lead bytes / lead bytes of multi-byte characters (byte positions)
+        int vhi, nvalid;                    // valid bytes: [vlo, vhi) of this thread's 32
         uint32_t acc0[4], acc1[4], acc2[4];
         {
             const uint4 q0 = *reinterpret_cast<const uint4 *>(tileS + wb0);
@@ -611,6 +636,7 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
             const long long rem = p.n_bytes - g0;
             vhi = rem <= 0 ? 0 : (rem >= 32 ? 32 : int(rem));
             const uint32_t valid = vhi > vlo ? (mask_lt(vhi) & ~mask_lt(vlo)) : 0u;
+            nvalid = vhi > vlo ? vhi - vlo : 0;
             lead = (leadbits & valid) | sb;
             mbl = leadbits & hib & valid;     // bytes >= 0xC0 inside the data
             // every byte through the feature LUT (bytes >= 0x80 and padding map to "no features")
@@ -659,19 +685,17 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
                 del &= keep;
             }
         }
+        PROF(1);
         const int n = __popc(lead);                     // characters of this thread (incl. the end-of-data terminator)
-        int c_end;
-        const int c0 = block_excl_sum(n, scratch, c_end, lane, warp);
-        leadmaskS[tid] = lead;
-        cprefS[tid] = c0;
-        if (tid == 0) cprefS[NT] = c_end;
 
-        // ------------------------------------------------------------------ phase 2a: context planes
-        // prev: last character of the previous thread; next/after-next: first two characters of the next thread
+        // ---- character-count scan + neighbour exchange (one barrier)
         const uint32_t myLB = n > 0 ? ((((P[PL_A] >> (n - 1)) & 1u)) | (((P[PL_N] >> (n - 1)) & 1u) << 1) |
                                        (((P[PL_LO] >> (n - 1)) & 1u) << 2) | (((P[PL_SP] >> (n - 1)) & 1u) << 3) |
-                                       (((P[PL_SY] >> (n - 1)) & 1u) << 4) | 32u)
+                                       (((P[PL_SY] >> (n - 1)) & 1u) << 4))
                                     : 0u;
+        int nscan = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, nscan, d); if (lane >= d) nscan += t; }
         uint32_t LB = __shfl_up_sync(FULL, myLB, 1);
         uint32_t XA = __shfl_down_sync(FULL, P[PL_A], 1), XN = __shfl_down_sync(FULL, P[PL_N], 1);
         uint32_t XLO = __shfl_down_sync(FULL, P[PL_LO], 1), XSP = __shfl_down_sync(FULL, P[PL_SP], 1);
@@ -681,8 +705,14 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
             uint32_t *e = edgeS + warp * 16;
             e[0] = P[PL_A]; e[1] = P[PL_N]; e[2] = P[PL_LO]; e[3] = P[PL_SP]; e[4] = P[PL_AT]; e[5] = P[PL_SL]; e[6] = Fm;
         }
-        if (lane == 31) edgeS[warp * 16 + 8] = myLB;
-        __syncthreads();  // (D) edges + cpref/leadmask visible
+        if (lane == 31) { edgeS[warp * 16 + 8] = myLB; scratch[warp] = nscan; }
+        leadmaskS[tid] = lead;
+        __syncthreads();  // (B)
+        int c0 = nscan - n, c_end = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) { const int t = scratch[w]; if (w < warp) c0 += t; c_end += t; }
+        cprefS[tid] = c0;
+        if (tid == 0) cprefS[NT] = c_end;
         if (lane == 31) {
             if (warp + 1 < NWARP) {
                 const uint32_t *e = edgeS + (warp + 1) * 16;
@@ -691,26 +721,15 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
         }
         if (lane == 0) LB = warp > 0 ? edgeS[(warp - 1) * 16 + 8] : 0u;
 
-        auto cidx = [&](int wb) -> int {  // characters starting at window bytes < wb
-            int t = wb >> 5;
-            if (t >= NT) return cprefS[NT];
-            return cprefS[t] + __popc(leadmaskS[t] & mask_lt(wb & 31));
-        };
-        const int c_lo = cprefS[FIRST_OWNED_THREAD];
-        long long own_end_g = (tile + 1) * (long long)TILE;
-        if (own_end_g > p.n_bytes) own_end_g = p.n_bytes;
-        const int c_hi = cidx(int(own_end_g - w0));
+        // ------------------------------------------------------------------ phase 2a: context planes + rules
         const bool term_in_win = p.n_bytes < w0 + WINB;
-        const int n_own = c_hi - c_lo;
-        // thread-local masks: real characters (not the terminator), owned, active (trusted forward context)
         const long long g0 = w0 + wb0;
         const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
         const uint32_t REAL = mask_lt(n - (has_term ? 1 : 0));
-        const uint32_t OWN = (tid >= FIRST_OWNED_THREAD && tid < END_OWNED_THREAD) ? REAL : 0u;
-        uint32_t ACT = tid >= FIRST_OWNED_THREAD ? REAL : 0u;
-        if (tid == NT - 1 && !term_in_win) ACT &= mask_lt(__popc(lead & mask_lt(32 - TRUST_MARGIN)));
+        // characters with complete forward context (everything but the last few bytes of the window)
+        uint32_t TRUST = tid >= FIRST_OWNED_THREAD ? REAL : 0u;
+        if (tid == NT - 1 && !term_in_win) TRUST &= mask_lt(__popc(lead & mask_lt(32 - TRUST_MARGIN)));
 
-        // 64-bit view "this thread's characters followed by the next thread's": shift right by 1 / 2
         auto next1 = [&](uint32_t X, uint32_t Xn) -> uint32_t {
             const uint32_t l = X | __funnelshift_lc(0u, Xn, n), h = __funnelshift_lc(Xn, 0u, n);
             return __funnelshift_r(l, h, 1);
@@ -722,6 +741,21 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
         const uint32_t Lm_raw = next1(Fm, XF);           // character ends a string (next one starts a string)
         const uint32_t L2m = next2(Fm, XF);
         const uint32_t nF = ~Lm_raw, aF = ~(Lm_raw | L2m), pF = ~Fm;
+        const uint32_t Sraw = P[PL_SP];
+
+        // ---- chunk-aligned ownership: the tile owns the characters from just after the first closer found in
+        // the SEARCH bytes after its nominal start up to (and including) the first closer found in the SEARCH
+        // bytes after its nominal end; both neighbours look at the same bytes, so they agree.
+        {
+            const uint32_t CLr = (Sraw | Lm_raw) & REAL;
+            // characters whose lead byte lies in [nominal boundary, nominal boundary + SEARCH)
+            uint32_t cand = 0; bool lo_side = false, hi_side = false;
+            if (tid >= FIRST_OWNED_THREAD && tid < FIRST_OWNED_THREAD + RHALO / 32) { lo_side = true; cand = CLr; if (tid == FIRST_OWNED_THREAD + RHALO / 32 - 1) cand &= mask_lt(__popc(lead & mask_lt(32 - TRUST_MARGIN))); }
+            if (tid >= END_OWNED_THREAD) { hi_side = true; cand = CLr; if (tid == NT - 1) cand &= mask_lt(__popc(lead & mask_lt(32 - TRUST_MARGIN))); }
+            const unsigned blo = __ballot_sync(FULL, lo_side && cand != 0u), bhi = __ballot_sync(FULL, hi_side && cand != 0u);
+            if (lo_side && cand != 0u && (blo & mask_lt(lane)) == 0u && tile > 0) { sc.c_lo = c0 + __ffs(cand); sc.lo_found = 1; }
+            if (hi_side && cand != 0u && (bhi & mask_lt(lane)) == 0u) { sc.c_hi = c0 + __ffs(cand); sc.hi_found = 1; }
+        }
         uint32_t full[25];
 #pragma unroll
         for (int f = 0; f < 12; ++f) full[f] = P[f];
@@ -740,7 +774,7 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
         full[24] = next2(P[PL_SL], XSL) & aF;                         // AFTER_NEXT_SLASH
 
         // ---- rules: split count, mark, sym (combine_matrix_rows 2-D, latok.c:318-341) as bit-sliced counters
-        uint32_t CNT[4], SYC[4], Mm;
+        uint32_t CNT[4], SYC[4], Mraw;
         if (kDefault) {
             // C_SPLIT: SPACE + SYMBOL + PREV_SYMBOL + UPPER*NEXT_LOWER + UPPER*PREV_LOWER (default_tokenizer.py:49-55)
             const uint32_t t1 = full[5], t2 = full[6], t3 = full[20], t4 = full[4] & full[17], t5 = full[4] & full[16];
@@ -752,8 +786,8 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
             CNT[2] = (c1 & c2) | (c3 & (c1 ^ c2));
             CNT[3] = 0;
             // C_MASK (default_tokenizer.py:80-91)
-            Mm = (full[7] & full[18] & full[13]) | (full[11] & full[18] & full[21] & full[23]) |
-                 (full[8] & full[14] & full[15]) | (full[9] & full[22] & full[24] & full[12]);
+            Mraw = (full[7] & full[18] & full[13]) | (full[11] & full[18] & full[21] & full[23]) |
+                   (full[8] & full[14] & full[15]) | (full[9] & full[22] & full[24] & full[12]);
             // C_SYM: SYMBOL*NEXT_SPACE (default_tokenizer.py:100-102)
             SYC[0] = full[6] & full[19]; SYC[1] = SYC[2] = SYC[3] = 0;
         } else {
@@ -769,16 +803,11 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
             };
 #pragma unroll
             for (int b = 0; b < 4; ++b) { CNT[b] = 0; SYC[b] = 0; }
-            Mm = 0;
+            Mraw = 0;
             for (int i = 0; i < p.rules.n_split; ++i) add1(CNT, term(p.rules.split[i]));
-            for (int i = 0; i < p.rules.n_mask; ++i) Mm |= term(p.rules.mask[i]);
+            for (int i = 0; i < p.rules.n_mask; ++i) Mraw |= term(p.rules.mask[i]);
             for (int i = 0; i < p.rules.n_sym; ++i) add1(SYC, term(p.rules.sym[i]));
         }
-        const uint32_t Sraw = P[PL_SP];
-        const uint32_t S = Sraw & ACT;
-        Mm &= ACT;
-        const uint32_t FmA = Fm & ACT, Lm = Lm_raw & ACT;
-
         if (kWords) {
             // per-character 25-bit words (+ FIRST / LAST flags) for the token-feature and matrix emitters
             uint32_t a[32];
@@ -792,26 +821,29 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
             for (int j = 0; j < 32; ++j)
                 if (j < n) wordS[widx(c0 + j)] = a[j];
         }
+        __syncthreads();  // (C) boundaries
+        PROF(2);
 
-        // local backlog function: +1 per mark, max(x-1,0) per space, reset at a string start
-        Fn f_act;
-        {
-            const uint32_t ev0 = Mm | FmA;
-            if (ev0 == 0u) { f_act.u = -__popc(S); f_act.v = 0; }
-            else {
-                f_act = fn_id();
-                uint32_t ev = ev0 | S;
-                while (ev) {
-                    const uint32_t b = ev & (0u - ev); ev &= ev - 1;
-                    if (FmA & b) { f_act.u = NEG; f_act.v = 0; }
-                    if (Mm & b) { f_act.u = max(f_act.u + 1, NEG); f_act.v = f_act.v + 1; }
-                    if (S & b) { f_act.u = max(f_act.u - 1, NEG); f_act.v = max(f_act.v - 1, 0); }
-                }
-            }
-        }
-        Fn excl, total;
-        block_excl_fn(f_act, scratch, excl, total, lane, warp);
-        if (tid == END_OWNED_THREAD) { sc.agg_u = excl.u; sc.agg_v = excl.v; }  // composition over the owned threads
+        auto cidx = [&](int wb) -> int {  // characters starting at window bytes < wb
+            int t = wb >> 5;
+            if (t >= NT) return cprefS[NT];
+            return cprefS[t] + __popc(leadmaskS[t] & mask_lt(wb & 31));
+        };
+        // tile-relative character indices of the owned range [c_lo, c_hi)
+        const bool last_tile = tile == p.ntiles - 1;
+        const int c_lo = sc.lo_found ? sc.c_lo : cprefS[FIRST_OWNED_THREAD];
+        int c_hi;
+        if (last_tile) c_hi = cidx(int(p.n_bytes - w0));
+        else c_hi = sc.hi_found ? sc.c_hi : cprefS[END_OWNED_THREAD];
+        const bool closed = last_tile || sc.hi_found;      // the owned range ends at a chunk closer
+        const int n_own = c_hi - c_lo;
+        const uint32_t OWN = range_mask(c0, c_lo, c_hi) & REAL;
+        // characters the block mask is evaluated on: the owned ones, plus (only when the last owned chunk is
+        // still open) the trusted halo, where it may close
+        const uint32_t ACT = closed ? OWN : (range_mask(c0, c_lo, 0x7FFFFFFF) & TRUST);
+        const uint32_t S = Sraw & ACT, Mm = Mraw & ACT, FmA = Fm & ACT, Lm = Lm_raw & ACT;
+        const uint32_t CL = S | Lm;        // characters that close a whitespace chunk
+
         // last string start among the owned characters (tile-relative), and for each thread the latest one before it
         int lf_excl;
         {
@@ -823,128 +855,261 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
             const int got = __shfl_sync(FULL, mine, src);
             lf_excl = below ? got : -1;
             const int wlast = __shfl_sync(FULL, mine, has ? 31 - __clz(has) : 0);
-            if (lane == 0) scratch[128 + warp] = has ? wlast : -1;
-        }
-        __syncthreads();  // (E)
-        {
-            int lfw = -1, lft = -1;
-#pragma unroll
-            for (int w = 0; w < NWARP; ++w) { const int v = scratch[128 + w]; if (w < warp) lfw = max(lfw, v); lft = max(lft, v); }
-            lf_excl = max(lf_excl, lfw);
-            if (tid == 0) sc.lf_tile = lft;
+            const int wfirst = __shfl_sync(FULL, FO ? c0 + __ffs(FO) - 1 : 0, has ? __ffs(has) - 1 : 0);
+            if (lane == 0) { scratch[128 + warp] = has ? wlast : -1; scratch[136 + warp] = has ? wfirst : 0x7FFFFFFF; }
+            // owned marks / spaces (for the backlog transfer function of the tile)
+            const int cm = __reduce_add_sync(FULL, __popc(Mraw & OWN)), cs = __reduce_add_sync(FULL, __popc(Sraw & OWN));
+            if (lane == 0) { scratch[144 + warp] = cm; scratch[152 + warp] = cs; }
         }
 
-        // ------------------------------------------------------------------ chain 1
-        if (warp == 0) {
+        auto is_split = [&](int c) -> bool {   // c = tile character index; thread-local planes live in splitS
+            int t = c >> 5;
+            while (t + 1 < NT && cprefS[t + 1] <= c) ++t;
+            return (splitS[t] >> (c - cprefS[t])) & 1u;
+        };
+        // feature sums of characters c, c-1, ... down to the token's first character (a split) or c_lo
+        auto walk_back = [&](int c, unsigned acc[7], bool &hit) {
+            hit = false;
+            for (; c >= c_lo; --c) {
+                const uint32_t w = wordS[widx(c)] & FEATMASK;
+#pragma unroll
+                for (int g = 0; g < 7; ++g) acc[g] = __vadd4(acc[g], spread4((w >> (4 * g)) & 15u));
+                if (is_split(c)) { hit = true; break; }
+            }
+        };
+        // feature sums of the token still open at the end of the owned range (one thread; token-feature mode)
+        auto publish_open_sums = [&]() {
+            unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit = false;
+            if (n_own > 0) walk_back(c_hi - 1, acc, hit);
+            uint4 a, b, c4;
+            a.x = hit ? 1u : 0u; a.y = a.z = a.w = 0;
+            b.x = acc[0]; b.y = acc[1]; b.z = acc[2]; b.w = acc[3];
+            c4.x = acc[4]; c4.y = acc[5]; c4.z = acc[6]; c4.w = 0;
+            uint4 *o = reinterpret_cast<uint4 *>(p.osum + tile);
+            st_rec(o, a); st_rec(o + 1, b); st_rec(o + 2, c4);
+        };
+        // ------------------------------------------------------------------ phase 2b/3 (speculative: no backlog enters)
+        uint32_t HOT = 0, Zm = 0, SPLIT = 0, E = 0, V[5];
+        int ntok_tile = 0, tp = 0, slow = 0;
+        int x_tile_in = 0;
+        for (int attempt = 0;; ++attempt) {
+            // ---- backlog relaxation: every thread starts from 0, carries are propagated until nothing changes
+            int xin = 0, out = 0, warp_seed = warp == 0 ? x_tile_in : 0, pub = 0;
+            if (Mm) out = eval_backlog(0, Mm, FmA, S, Lm, HOT); else HOT = 0;
+            for (;;) {
+                for (;;) {
+                    int nx = __shfl_up_sync(FULL, out, 1);
+                    if (lane == 0) nx = warp_seed;
+                    const bool ch = nx != xin;
+                    if (!__any_sync(FULL, ch)) break;
+                    if (ch) { xin = nx; if (xin != 0 || Mm) out = eval_backlog(xin, Mm, FmA, S, Lm, HOT); else { out = 0; HOT = 0; } }
+                }
+                const int o31 = __shfl_sync(FULL, out, 31);
+                const bool ch = o31 != pub;
+                pub = o31;
+                if (lane == 31) scratch[64 + warp] = o31;
+                if (!__syncthreads_or(ch ? 1 : 0)) break;   // (D)
+                const int seed = warp > 0 ? scratch[64 + warp - 1] : x_tile_in;
+                __syncthreads();
+                warp_seed = seed;
+            }
+            // backlog after the last owned character (tile transfer function at 0) and at the end of ACT
+            if (closed) { if (tid == NT - 1) { sc.v_tile = out; sc.x_end = out; } }
+            else { if (tid == END_OWNED_THREAD - 1) sc.v_tile = out; if (tid == NT - 1) sc.x_end = out; }
+
+            // ---- blank the chunks whose closer is hot: flood HOT downwards to the previous closer
+            Zm = HOT;
+            {
+                uint32_t pr = ~CL;
+                Zm |= pr & (Zm >> 1); pr &= pr >> 1;
+                Zm |= pr & (Zm >> 2); pr &= pr >> 2;
+                Zm |= pr & (Zm >> 4); pr &= pr >> 4;
+                Zm |= pr & (Zm >> 8); pr &= pr >> 8;
+                Zm |= pr & (Zm >> 16);
+            }
+            const bool hasCL = CL != 0u;
+            const bool firstHot = hasCL && (HOT & (CL & (0u - CL))) != 0u;
+            int cin;
+            {
+                const unsigned H = __ballot_sync(FULL, hasCL), FH = __ballot_sync(FULL, firstHot);
+                if (lane == 0) { scratch[80 + 2 * warp] = H != 0u; scratch[80 + 2 * warp + 1] = H ? ((FH >> (__ffs(H) - 1)) & 1u) : 0u; }
+                // an owned range that does not end at a closer: the last owned chunk may need the look-ahead walk
+                if (!closed && warp == NWARP - 1) {
+                    const unsigned above = lane == 31 ? 0u : (H & (0xFFFFFFFFu << (lane + 1)));
+                    if (tid == END_OWNED_THREAD - 1) {
+                        const int nr = __popc(ACT);
+                        if (nr > 0 && ((CL >> (nr - 1)) & 1u) == 0u && above == 0u) sc.need_walk = 1;
+                    }
+                }
+                __syncthreads();  // (E)
+                const unsigned above = lane == 31 ? 0u : (H & (0xFFFFFFFFu << (lane + 1)));
+                if (above) cin = (FH >> (__ffs(above) - 1)) & 1u;
+                else {
+                    cin = 2;
+                    for (int w2 = warp + 1; w2 < NWARP; ++w2)
+                        if (scratch[80 + 2 * w2]) { cin = scratch[80 + 2 * w2 + 1]; break; }
+                }
+            }
+            if (sc.need_walk) {
+                if (sc.x_end >= 1) { if (tid == 0) sc.far = 1; }
+                else if (warp == 0) {
+                    bool any = walk_ahead(p, tb, w0 + WINB - TRUST_MARGIN, lane);
+                    if (lane == 0) { sc.far = any ? 1 : 0; if (attempt == 0) atomicAdd(&p.result->walks, 1ull); }
+                }
+                __syncthreads();
+            }
+            if (cin == 1 || (cin == 2 && sc.far)) {
+                const uint32_t top = hasCL ? ~((2u << (31 - __clz(CL))) - 1u) : 0xFFFFFFFFu;
+                Zm |= top;
+            }
+
+            // ---- split values: splits = split_cnt * block_mask + sym; splits[0] = 1 (default_tokenizer.py:121-132)
+            const uint32_t keepm = ~Zm | Sraw;             // block mask = 1
+            {
+                uint32_t carry = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t x = CNT[b] & keepm, y = SYC[b];
+                    V[b] = x ^ y ^ carry;
+                    carry = (x & y) | (carry & (x ^ y));
+                }
+                V[4] = carry;
+                V[0] |= Fm;
+#pragma unroll
+                for (int b = 1; b < 5; ++b) V[b] &= ~Fm;
+            }
+            SPLIT = V[0] | V[1] | V[2] | V[3] | V[4];
+            const uint32_t PS = (Sraw << 1) | ((LB >> 3) & 1u);                // previous character is a space
+            E = ((SPLIT & ~Sraw) | (~SPLIT & PS & ~Fm)) & OWN;                 // a token is counted at this character
+            int tscan = __popc(E);
+            const int mytok = tscan;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, tscan, d); if (lane >= d) tscan += t; }
+            if (lane == 31) scratch[96 + warp] = tscan;
+            emitS[tid] = E; splitS[tid] = SPLIT;
+            slow = __syncthreads_or((want_splits && nvalid == 32 && n < 4) ? 1 : 0);  // (F) malformed UTF-8 only
+            tp = tscan - mytok; ntok_tile = 0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) { const int t = scratch[96 + w]; if (w < warp) tp += t; ntok_tile += t; }
+
+            if (attempt == 1) break;
+            // ================================================================ publish aggregate, look back
+            if (warp == 0) {
+                int lft = -1, cm = 0, cs = 0;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w) { lft = max(lft, scratch[128 + w]); cm += scratch[144 + w]; cs += scratch[152 + w]; }
+                const int v_tile = sc.v_tile;
+                if (lane == 0) {
+                    uint4 r;
+                    r.x = (p.epoch << 2) | 1u;
+                    r.y = (unsigned)n_own | ((lft >= 0 ? (unsigned)(lft - c_lo + 1) : 0u) << 16);
+                    r.z = (unsigned)ntok_tile | ((unsigned)v_tile << 16);
+                    r.w = (unsigned)(lft >= 0 ? NEG : cm - cs);
+                    if (kWords && want_feats) { publish_open_sums(); __threadfence(); }
+                    st_rec(p.agg + tile, r);
+                }
+                const Prefix pre = lookback(tile, p, lane);
+                if (lane == 0) { sc.G_in = pre.G; sc.base_in = pre.base; sc.K_in = pre.K; sc.x_in = pre.x; }
+            }
+            __syncthreads();  // (G)
+            if (sc.x_in == 0) break;
+            // a backlog does enter this tile (rare): redo the block mask with it
+            x_tile_in = sc.x_in;
+            if (tid == 0) { sc.need_walk = 0; sc.far = 0; }
+            __syncthreads();
+        }
+        PROF(3);
+        {   // latest owned string start in the warps before this one
+            int lfw = -1;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) if (w < warp) lfw = max(lfw, scratch[128 + w]);
+            lf_excl = max(lf_excl, lfw);
+        }
+        const unsigned long long G_in = sc.G_in, K_in = sc.K_in;
+        // publish the inclusive prefix
+        if (tid == 0) {
             int lft = -1;
 #pragma unroll
             for (int w = 0; w < NWARP; ++w) lft = max(lft, scratch[128 + w]);
-            Chain1 a;
-            a.n = (unsigned long long)n_own;
-            a.has = lft >= 0 ? 1u : 0u;
-            a.lf = a.has ? (unsigned long long)(lft - c_lo) : 0ull;
-            a.u = sc.agg_u; a.v = sc.agg_v; a.reset = 0;
-            if (lane == 0) publish(p.agg1 + tile, p.status1 + tile, a, p.epoch, 1u);
-            Chain1 pre = lookback<Chain1>(tile, p.status1, p.agg1, p.inc1, p.epoch, p.result, lane);
-            if (lane == 0) {
-                Chain1 inc = combine1(pre, a);
-                inc.reset = 1;
-                publish(p.inc1 + tile, p.status1 + tile, inc, p.epoch, 2u);
-                sc.G_in = pre.n; sc.base_in = pre.lf; sc.x_in = pre.v;
-                sc.x_end = fn_apply(total, pre.v);
-            }
-        }
-        __syncthreads();  // (F)
-        const unsigned long long G_in = sc.G_in;
-        const int x_t = fn_apply(excl, sc.x_in);
-
-        // ------------------------------------------------------------------ phase 2b: block mask
-        const uint32_t CL = S | Lm;        // characters that close a whitespace chunk
-        uint32_t HOT = 0;                  // closers whose chunk is blanked (backlog >= 1 at the closer)
-        if (x_t != 0 || Mm != 0u) {
-            int x = x_t; uint32_t ev = Mm | S | FmA | Lm;
-            while (ev) {
-                const uint32_t b = ev & (0u - ev); ev &= ev - 1;
-                if (FmA & b) x = 0;
-                if (Mm & b) ++x;
-                if ((CL & b) && x >= 1) HOT |= b;
-                if (S & b) x = max(x - 1, 0);
-            }
-        }
-        uint32_t Zm = HOT;
-        {
-            uint32_t pr = ~CL;
-            Zm |= pr & (Zm >> 1); pr &= pr >> 1;
-            Zm |= pr & (Zm >> 2); pr &= pr >> 2;
-            Zm |= pr & (Zm >> 4); pr &= pr >> 4;
-            Zm |= pr & (Zm >> 8); pr &= pr >> 8;
-            Zm |= pr & (Zm >> 16);
-        }
-        const bool hasCL = CL != 0u;
-        const bool firstHot = hasCL && (HOT & (CL & (0u - CL))) != 0u;
-        int cin;
-        {
-            const unsigned H = __ballot_sync(FULL, hasCL), FH = __ballot_sync(FULL, firstHot);
-            if (lane == 0) { scratch[64 + 2 * warp] = H != 0u; scratch[64 + 2 * warp + 1] = H ? ((FH >> (__ffs(H) - 1)) & 1u) : 0u; }
-            __syncthreads();  // (G)
-            const unsigned above = lane == 31 ? 0u : (H & (0xFFFFFFFFu << (lane + 1)));
-            if (above) cin = (FH >> (__ffs(above) - 1)) & 1u;
-            else {
-                cin = 2;
-                for (int w2 = warp + 1; w2 < NWARP; ++w2)
-                    if (scratch[64 + 2 * w2]) { cin = scratch[64 + 2 * w2 + 1]; break; }
-            }
-        }
-        // the whitespace chunk open at the end of the owned range: closed inside the halo, or walk ahead
-        if (tid == END_OWNED_THREAD - 1 && !term_in_win) {
-            const int nr = __popc(ACT);
-            const bool open = nr > 0 && ((CL >> (nr - 1)) & 1u) == 0u && cin == 2;
-            if (open) sc.need_walk = 1;
-        }
-        __syncthreads();  // (H)
-        if (sc.need_walk) {
-            if (sc.x_end >= 1) { if (tid == 0) sc.far = 1; }
-            else if (warp == 0) {
-                bool any = walk_ahead(p, tb, w0 + WINB - TRUST_MARGIN, lane);
-                if (lane == 0) { sc.far = any ? 1 : 0; atomicAdd(&p.result->walks, 1ull); }
-            }
-            __syncthreads();
-        }
-        if (cin == 1 || (cin == 2 && sc.far)) {
-            const uint32_t top = hasCL ? ~((2u << (31 - __clz(CL))) - 1u) : 0xFFFFFFFFu;
-            Zm |= top;
+            if (kWords && want_feats && x_tile_in != 0) publish_open_sums();
+            IncRec *ir = p.inc + tile;
+            uint4 a, b;
+            const unsigned long long Gn = G_in + (unsigned long long)n_own, Kn = K_in + (unsigned long long)ntok_tile;
+            const unsigned long long Bn = lft >= 0 ? G_in + (unsigned long long)(lft - c_lo) : sc.base_in;
+            a.x = (unsigned)Gn; a.y = (unsigned)(Gn >> 32); a.z = (unsigned)Bn; a.w = (unsigned)(Bn >> 32);
+            b.x = (unsigned)Kn; b.y = (unsigned)(Kn >> 32); b.z = (unsigned)sc.v_tile; b.w = 0;
+            st_rec(ir, a); st_rec(reinterpret_cast<uint4 *>(ir) + 1, b);
+            __threadfence();
+            uint4 r = ld_rec(p.agg + tile);
+            r.x = (p.epoch << 2) | 2u;
+            st_rec(p.agg + tile, r);
         }
 
-        // ------------------------------------------------------------------ phase 3: split values, token flags
-        // splits = split_cnt * block_mask + sym; splits[0] = 1   (default_tokenizer.py:121-132), bit-sliced
-        const uint32_t keepm = ~Zm | Sraw;             // block mask = 1
-        uint32_t V[5];
-        {
-            uint32_t carry = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t x = CNT[b] & keepm, y = SYC[b];
-                V[b] = x ^ y ^ carry;
-                carry = (x & y) | (carry & (x ^ y));
-            }
-            V[4] = carry;
-            V[0] |= Fm;
-#pragma unroll
-            for (int b = 1; b < 5; ++b) V[b] &= ~Fm;
-        }
-        const uint32_t SPLIT = V[0] | V[1] | V[2] | V[3] | V[4];
-        const uint32_t PS = (Sraw << 1) | ((LB >> 3) & 1u);                // previous character is a space
-        const uint32_t E = ((SPLIT & ~Sraw) | (~SPLIT & PS & ~Fm)) & OWN;  // a token is counted at this character
-        const uint32_t EW = SPLIT & ~Fm & ~PS & OWN;                       // this split ends the previous token
-        const uint32_t EL = Lm & ~Sraw & OWN;                              // end of string ends the last token
-        int ntok_tile;
-        const int tp = block_excl_sum(__popc(E), scratch, ntok_tile, lane, warp);
-        emitS[tid] = E; tokprefS[tid] = tp; splitS[tid] = SPLIT;
+        // ------------------------------------------------------------------ phase 4: staging
+        tokprefS[tid] = tp;
         if (tid == 0) tokprefS[NT] = ntok_tile;
-
-        // split values -> bytes -> staging buffer at (tile-relative character index + G_in % 16), so that the
-        // staging buffer and the global split mask share their 16-byte alignment
-        const int a16 = int(G_in & 15ull);
+        // string-relative index = tile character index - cbase; for the string that began before this tile
+        // cbase = -(characters of it before the tile) - c_lo ... folded in as `delta` below
+        const long long delta_ll = (long long)(G_in - sc.base_in) - (long long)c_lo;     // idx = c + delta
+        const int delta = (int)delta_ll;
+        const bool stage_ok = ntok_tile <= SPAN_STAGE - 1 && K_in + (unsigned long long)ntok_tile <= (unsigned long long)p.cap_tokens;
+        if (K_in + (unsigned long long)ntok_tile > (unsigned long long)p.cap_tokens && tid == 0) atomicOr(&p.result->error, 4u);
+        if (want_spans) {
+            // one (start, end) pair per token; end = next split (a string start is always a split)
+            // first split of each following thread, for tokens that run past this thread's characters
+            // splits that may end a token of this tile: owned ones, plus (closed range) the string start right after it
+            const uint32_t SPq = SPLIT & mask_lt(n) & range_mask(c0, c_lo, closed ? c_hi + 1 : c_hi);
+            const int myfirst = SPq ? c0 + __ffs(SPq) - 1 : -1;
+            {
+                const unsigned hs = __ballot_sync(FULL, myfirst >= 0);
+                const int wf = __shfl_sync(FULL, myfirst, hs ? __ffs(hs) - 1 : 0);
+                if (lane == 0) scratch[160 + warp] = hs ? wf : -1;
+            }
+            __syncthreads();  // (H)
+            int nextsplit;     // tile index of the first split in the following threads (-1: none in this window)
+            {
+                const unsigned hs = __ballot_sync(FULL, myfirst >= 0);
+                const unsigned above = lane == 31 ? 0u : (hs & (0xFFFFFFFFu << (lane + 1)));
+                const int got = __shfl_sync(FULL, myfirst, above ? __ffs(above) - 1 : 0);
+                nextsplit = above ? got : -1;
+                if (!above) for (int w2 = warp + 1; w2 < NWARP; ++w2) if (scratch[160 + w2] >= 0) { nextsplit = scratch[160 + w2]; break; }
+            }
+            uint32_t ev = E;
+            int rank = 0;
+            int cbase = lf_excl >= 0 ? lf_excl : -delta;     // idx = c - cbase
+            while (ev) {
+                const int i = __ffs(ev) - 1; ev &= ev - 1;
+                const uint32_t fb = Fm & OWN & mask_lt(i + 1);
+                if (fb) cbase = c0 + 31 - __clz(fb);
+                const uint32_t ab = (i == 31) ? 0u : (SPq & (0xFFFFFFFEu << i));
+                const int endc = ab ? c0 + __ffs(ab) - 1 : nextsplit;
+                const int sidx = c0 + i - (((SPLIT >> i) & 1u) ? 0 : 1) - cbase;
+                const int eidx = endc >= 0 ? endc - cbase : -1;
+                const int lord = tp + rank;
+                if (stage_ok) spanS[1 + lord] = make_int2(sidx, eidx);
+                else {
+                    const long long k = (long long)K_in + lord;
+                    if (k < p.cap_tokens) { p.spans[2 * k] = sidx; if (eidx >= 0) p.spans[2 * k + 1] = eidx; }
+                }
+                ++rank;
+            }
+            // the first split of the tile that follows a non-space character ends the token left open by earlier tiles
+            {
+                const uint32_t PSr = (Sraw << 1) | ((LB >> 3) & 1u);
+                // (in the last tile the end-of-data terminator counts: it ends the last token of the data)
+                const uint32_t END = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo, last_tile ? c_hi + 1 : c_hi);
+                if (END) {
+                    const int i = __ffs(END) - 1;
+                    if (tp + __popc(E & mask_lt(i)) == 0) {
+                        const uint32_t fb = Fm & OWN & mask_lt(i);      // string starts strictly before the split
+                        const int cb = fb ? c0 + 31 - __clz(fb) : (lf_excl >= 0 ? lf_excl : -delta);
+                        const long long k = (long long)K_in - 1;
+                        if (k >= 0 && k < p.cap_tokens) p.spans[2 * k + 1] = c0 + i - cb;
+                    }
+                }
+            }
+        }
+        // split values -> bytes -> staging buffer at VPAD + (tile character index - c_lo)
         if (want_splits) {
             uint32_t W[8];
             if (kDefault) {
@@ -968,31 +1133,24 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
                     W[g] = w;
                 }
             }
-            // the 4 bytes before this thread's first character (tail of the previous thread)
-            uint32_t tailw = 0;
-            {
-                const int nr = n;   // terminator value bytes are harmless: they are never copied out
-                if (nr >= 4) {
-                    const int sft = nr - 4;
-                    uint32_t w = 0;
+            uint32_t tailw = 0;       // the last 4 characters of this thread, for the next thread's first word
+            if (n >= 4) {
+                const int sft = n - 4;
 #pragma unroll
-                    for (int b = 0; b < 5; ++b) w += spread4((V[b] >> sft) & 15u) << b;
-                    tailw = w;
-                }
+                for (int b = 0; b < 5; ++b) tailw += spread4((V[b] >> sft) & 15u) << b;
             }
             uint32_t headw = __shfl_up_sync(FULL, tailw, 1);
             if (lane == 31) edgeS[warp * 16 + 9] = tailw;
-            const bool shortn = (n < 4) && (tid >= FIRST_OWNED_THREAD - 1) && (tid <= END_OWNED_THREAD) && g0 < p.n_bytes && g0 + 32 > 0;
-            const int slow = __syncthreads_or(shortn ? 1 : 0);  // (I0) also publishes edgeS[..+9]
+            __syncthreads();  // (I0)
             if (lane == 0) headw = warp > 0 ? edgeS[(warp - 1) * 16 + 9] : 0u;
-            const int o = c0 - c_lo + a16;                 // staging offset of this thread's first character
-            if (tid >= FIRST_OWNED_THREAD && tid <= END_OWNED_THREAD && o >= 0) {
+            const int o = VPAD + c0 - c_lo;                 // staging offset of this thread's first character
+            if (tid >= FIRST_OWNED_THREAD && o >= 4 && n > 0) {
                 if (!slow) {
                     // words are written by the thread that owns their LAST byte: no partial words, no races
                     const int s = o & 3;
                     const int cnt = (s + n) >> 2;
                     uint32_t *dst = reinterpret_cast<uint32_t *>(valS) + (o >> 2);
-                    const int sh = 32 - 8 * s;             // stream = [headw, W0..W7]; word i starts s bytes before W[i-1]'s end
+                    const int sh = 32 - 8 * s;
                     uint32_t prev = headw;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -1001,14 +1159,13 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
                         prev = W[i];
                     }
                     if (8 < cnt) dst[8] = __funnelshift_r(prev, 0u, sh);
-                    // the thread that holds the end-of-data terminator flushes the trailing partial word byte by byte
-                    // (bytes before this thread's first character come from the previous thread's tail word)
-                    if (has_term) {
-                        const int end = o + n - 1;               // staging position just after the last real character
+                    // the thread that holds the last owned character flushes the trailing partial word byte by byte
+                    if (c0 < c_hi && c0 + n >= c_hi) {
+                        const int end = VPAD + n_own;
                         for (int q = end & ~3; q < end; ++q) {
                             const int j = q - o;
                             const uint32_t src = j >= 0 ? W[j >> 2] >> ((j & 3) * 8) : headw >> ((4 + j) * 8);
-                            if (q >= 0) valS[q] = (uint8_t)(src & 0xFFu);
+                            valS[q] = (uint8_t)(src & 0xFFu);
                         }
                     }
                 } else {
@@ -1021,69 +1178,66 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
                 }
             }
         }
-        __syncthreads();  // (I)
-
-        auto is_split = [&](int c) -> bool {   // c = tile character index; thread-local planes live in splitS
-            // find the thread that holds character c: threads hold at least 8 characters each in valid UTF-8
-            int t = c >> 5;
-            while (t + 1 < NT && cprefS[t + 1] <= c) ++t;
-            return (splitS[t] >> (c - cprefS[t])) & 1u;
-        };
-        // feature sums of characters c, c-1, ... down to the token's first character (a split) or c_lo
-        auto walk_back = [&](int c, unsigned acc[7], bool &hit) {
-            hit = false;
-            for (; c >= c_lo; --c) {
-                const uint32_t w = wordS[widx(c)] & FEATMASK;
-#pragma unroll
-                for (int g = 0; g < 7; ++g) acc[g] = __vadd4(acc[g], spread4((w >> (4 * g)) & 15u));
-                if (is_split(c)) { hit = true; break; }
-            }
-        };
+        __syncthreads();  // (I) staging complete
+        PROF(4);
         if (kWords && want_feats) {
-            if (n_own > 0 && tid == END_OWNED_THREAD) {
+            // every split that follows a non-space character ends a token: sum the feature words back to its start
+            const uint32_t PSr = (Sraw << 1) | ((LB >> 3) & 1u);
+            uint32_t ev = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo, last_tile ? c_hi + 1 : c_hi);
+            while (ev) {
+                const int i = __ffs(ev) - 1; ev &= ev - 1;
+                const long long k = (long long)K_in + tp + __popc(E & mask_lt(i)) - 1;
+                if (k < 0 || k >= p.cap_tokens) continue;
                 unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit;
-                walk_back(c_hi - 1, acc, hit);
-                sc.open_has = hit ? 1u : 0u;
-                for (int g = 0; g < 7; ++g) sc.open_sums[g] = acc[g];
-                sc.open_sums[7] = 0;
+                walk_back(c0 + i - 1, acc, hit);
+                for (long long t = tile - 1; !hit && t >= 0; --t) {      // token began in an earlier tile
+                    const uint4 *o = reinterpret_cast<const uint4 *>(p.osum + t);
+                    const uint4 a = ld_rec(o), b = ld_rec(o + 1), c4 = ld_rec(o + 2);
+                    acc[0] = __vadd4(acc[0], b.x); acc[1] = __vadd4(acc[1], b.y); acc[2] = __vadd4(acc[2], b.z);
+                    acc[3] = __vadd4(acc[3], b.w); acc[4] = __vadd4(acc[4], c4.x); acc[5] = __vadd4(acc[5], c4.y);
+                    acc[6] = __vadd4(acc[6], c4.z);
+                    hit = a.x != 0u;
+                }
+                int8_t *row = p.feats + k * NFEAT;
+                for (int f = 0; f < NFEAT; ++f) row[f] = (int8_t)((acc[f >> 2] >> ((f & 3) * 8)) & 0xFFu);
             }
-            __syncthreads();
         }
 
-        // ------------------------------------------------------------------ chain 2
-        if (warp == 0) {
-            Chain2 a;
-            a.k = (unsigned long long)ntok_tile; a.reset = 0;
-            a.has_split = (kWords && want_feats) ? sc.open_has : 0u;
-            for (int g = 0; g < 8; ++g) a.sums[g] = (kWords && want_feats && n_own > 0) ? sc.open_sums[g] : 0u;
-            if (lane == 0) publish(p.agg2 + tile, p.status2 + tile, a, p.epoch, 1u);
-            Chain2 pre = lookback<Chain2>(tile, p.status2, p.agg2, p.inc2, p.epoch, p.result, lane);
-            if (lane == 0) {
-                Chain2 inc = combine2(pre, a);
-                inc.reset = 1;
-                publish(p.inc2 + tile, p.status2 + tile, inc, p.epoch, 2u);
-                sc.K_in = pre.k;
-                for (int g = 0; g < 8; ++g) sc.carry_sums[g] = pre.sums[g];
-            }
-        }
-        // split mask out while warp 0 looks back: 16-byte chunks, byte-wise at the two ragged ends
+        // ------------------------------------------------------------------ phase 5: coalesced output
         if (want_splits && n_own > 0) {
-            int8_t *dst = p.splits + G_in;                  // dst[j] <-> valS[a16 + j]
-            const int head = (16 - a16) & 15;               // bytes before the first 16-byte boundary
+            // dst[j] <-> valS[VPAD + j]; 16-byte global chunks are assembled from the (differently aligned) staging words
+            int8_t *dst = p.splits + G_in;
+            const int a16 = int(G_in & 15ull);
+            const int head = (16 - a16) & 15;
             const int nh = head < n_own ? head : n_own;
-            if (tid < nh) dst[tid] = (int8_t)valS[a16 + tid];
+            if (tid < nh) dst[tid] = (int8_t)valS[VPAD + tid];
             const int nchunks = (n_own - nh) >> 4;
-            const uint4 *src = reinterpret_cast<const uint4 *>(valS + a16 + nh);
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(valS);
+            const int sbyte = VPAD + nh;                    // staging byte of chunk 0
+            const int shb = 8 * (sbyte & 3);
             uint4 *d4 = reinterpret_cast<uint4 *>(dst + nh);
-            for (int i = tid; i < nchunks; i += NT) d4[i] = src[i];
+            for (int i = tid; i < nchunks; i += NT) {
+                const uint32_t *q = sw + ((sbyte + 16 * i) >> 2);
+                uint4 v;
+                if (shb == 0) { v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3]; }
+                else {
+                    const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+                    v.x = __funnelshift_r(q0, q1, shb); v.y = __funnelshift_r(q1, q2, shb);
+                    v.z = __funnelshift_r(q2, q3, shb); v.w = __funnelshift_r(q3, q4, shb);
+                }
+                d4[i] = v;
+            }
             const int done = nh + (nchunks << 4);
-            if (tid < n_own - done) dst[done + tid] = (int8_t)valS[a16 + done + tid];
+            if (tid < n_own - done) dst[done + tid] = (int8_t)valS[VPAD + done + tid];
         }
-        if (tid == NT - 1 && ntok_tile >= 1 && ntok_tile <= SPAN_STAGE - 1) spanS[2 * (ntok_tile - 1) + 3] = -1;  // "still open"
-        __syncthreads();  // (J)
-        const unsigned long long K_in = sc.K_in;
-
-        // ------------------------------------------------------------------ phase 4: emission
+        if (want_spans && stage_ok) {
+            int2 *dst = reinterpret_cast<int2 *>(p.spans) + K_in;
+            for (int i = tid; i < ntok_tile; i += NT) {
+                int2 v = spanS[1 + i];
+                if (v.y >= 0) dst[i] = v;
+                else p.spans[2 * (K_in + i)] = v.x;
+            }
+        }
         if (kWords && want_matrix) {
             int8_t *dst = p.matrix + G_in * NFEAT;
             const int nb = n_own * NFEAT;
@@ -1092,84 +1246,26 @@ __global__ void __launch_bounds__(NT) tokenize_kernel(const Params p)
                 dst[j] = (int8_t)((wordS[widx(c_lo + c)] >> f) & 1u);
             }
         }
-        const bool stage = want_spans && ntok_tile <= SPAN_STAGE - 1 && K_in + (unsigned long long)ntok_tile <= (unsigned long long)p.cap_tokens;
-        if (want_spans || want_feats) {
-            // string-relative index of character c: (G_in + c - c_lo) - (global index of its string's first character)
-            unsigned long long gbase = lf_excl >= 0 ? G_in + (unsigned long long)(lf_excl - c_lo) : sc.base_in;
-            uint32_t ev = (E | EW | EL | Fm) & OWN;
-            int rank = 0;  // tokens counted at earlier characters of this thread
-            const bool over = K_in + (unsigned long long)ntok_tile > (unsigned long long)p.cap_tokens;
-            if (over && tid == 0) atomicOr(&p.result->error, 4u);
-            while (ev) {
-                const int i = __ffs(ev) - 1; const uint32_t b = 1u << i; ev &= ev - 1;
-                const int c = c0 + i;
-                const unsigned long long g = G_in + (unsigned long long)(c - c_lo);
-                if (Fm & b) gbase = g;
-                const int idx = (int)(g - gbase);
-                const int lord = tp + rank;                        // tile-local ordinal of the token counted here
-                const long long ordx = (long long)K_in + lord;     // tokens counted before this character
-                if (EW & b) {  // previous token [.., idx)
-                    const long long k = ordx - 1;
-                    if (k >= 0 && k < p.cap_tokens) {
-                        if (want_spans) { if (stage && lord >= 1) spanS[2 * (lord - 1) + 3] = idx; else p.spans[2 * k + 1] = idx; }
-                        if (kWords && want_feats) {
-                            unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit;
-                            walk_back(c - 1, acc, hit);
-                            if (!hit) for (int q = 0; q < 7; ++q) acc[q] = __vadd4(acc[q], sc.carry_sums[q]);
-                            int8_t *row = p.feats + k * NFEAT;
-                            for (int f = 0; f < NFEAT; ++f) row[f] = (int8_t)((acc[f >> 2] >> ((f & 3) * 8)) & 0xFFu);
-                        }
-                    }
-                }
-                if (E & b) {
-                    const int sidx = (SPLIT & b) ? idx : idx - 1;
-                    if (want_spans && ordx < p.cap_tokens) { if (stage) spanS[2 * lord + 2] = sidx; else p.spans[2 * ordx] = sidx; }
-                    ++rank;
-                }
-                if (EL & b) {  // last token of the string [.., idx + 1)
-                    const int ll = tp + rank - 1;
-                    const long long k = (long long)K_in + ll;
-                    if (k >= 0 && k < p.cap_tokens) {
-                        if (want_spans) { if (stage && ll >= 0) spanS[2 * ll + 3] = idx + 1; else p.spans[2 * k + 1] = idx + 1; }
-                        if (kWords && want_feats) {
-                            unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit;
-                            walk_back(c, acc, hit);
-                            if (!hit) for (int q = 0; q < 7; ++q) acc[q] = __vadd4(acc[q], sc.carry_sums[q]);
-                            int8_t *row = p.feats + k * NFEAT;
-                            for (int f = 0; f < NFEAT; ++f) row[f] = (int8_t)((acc[f >> 2] >> ((f & 3) * 8)) & 0xFFu);
-                        }
-                    }
-                }
-            }
-        }
-        // per-string CSR offsets for the strings that start in the owned byte range
+        // per-string CSR offsets for the strings whose first character position is owned by this tile
         {
-            const long long s_end = p.tile_first_str[tile + 1];
-            for (long long s = p.tile_first_str[tile] + tid; s < s_end; s += NT) {
-                const int wb = int(p.offsets[s] - w0);
+            const long long wend = w0 + WINB;
+            for (long long s = p.tile_first_str[tile] + tid; s <= p.n_strings; s += NT) {
+                const long long o = p.offsets[s];
+                if (o >= wend) break;
+                const int wb = int(o - w0);
                 const int c = cidx(wb);
+                const bool mine = last_tile ? (c >= c_lo) : (c >= c_lo && c < c_hi);
+                if (!mine && !(tile == 0 && c < c_lo)) continue;
                 p.char_off[s] = (long long)(G_in + (unsigned long long)(c - c_lo));
                 const int t = wb >> 5;
                 p.tok_off[s] = (long long)K_in + tokprefS[t] + __popc(emitS[t] & mask_lt(c - cprefS[t]));
             }
         }
-        if (tile == p.ntiles - 1 && tid == 0) {
+        if (last_tile && tid == 0) {
             p.result->n_chars = G_in + (unsigned long long)n_own;
             p.result->n_tokens = K_in + (unsigned long long)ntok_tile;
         }
-        if (stage) {
-            // staged spans -> global, 8-byte pairs (the end of the token open at the tile end is written by a later tile;
-            // the end of the token open at the tile start, staged in slot -1, goes to token K_in - 1)
-            __syncthreads();
-            int2 *dst = reinterpret_cast<int2 *>(p.spans) + K_in;
-            const int2 *src = reinterpret_cast<const int2 *>(spanS) + 1;
-            // the last staged token may still be open (its end is written by a later tile): write only its start
-            for (int i = tid; i < ntok_tile; i += NT) {
-                const int2 v = src[i];
-                if (v.y >= 0) dst[i] = v;
-                else p.spans[2 * (K_in + i)] = v.x;
-            }
-        }
+        PROF(5);
     }
 }
 
