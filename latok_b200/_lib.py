@@ -7,10 +7,11 @@ with nvcc, and if it cannot be built or no CUDA device is present every compute 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "liblatok_b200.so"
+LIB_PATH = Path(os.environ.get("LATOK_B200_LIB") or PKG / "liblatok_b200.so")  # override: development builds only
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, EINTERNAL = range(6)
 SPLITS, SPANS, FEATS, MATRIX = 1, 2, 4, 8

@@ -52,6 +52,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     cmd = [find_nvcc(), *NVCC_FLAGS]
     if os.environ.get("LATOK_PROFILE"):
         cmd += ["-DLATOK_PROFILE"]
+    if os.environ.get("LATOK_DEFS"):
+        cmd += os.environ["LATOK_DEFS"].split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [str(s) for s in SOURCES] + ["-o", str(LIB)]

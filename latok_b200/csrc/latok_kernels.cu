@@ -31,7 +31,7 @@ constexpr int NEG = -(1 << 28);           // "-infinity" of the (max,+) backlog 
 constexpr unsigned SPIN_LIMIT = 1u << 27; // watchdog for look-back spins
 
 // ---- small helpers ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mask_lt(int k) { return k >= 32 ? 0xFFFFFFFFu : (k <= 0 ? 0u : ((1u << k) - 1u)); }
+__device__ __forceinline__ uint32_t mask_lt(int k) { return __funnelshift_lc(0xFFFFFFFFu, 0u, (unsigned)max(k, 0)); }  // low k bits (k clamped to 0..32)
 // bits of a thread's 32-character word that fall inside the character range [lo, hi)
 __device__ __forceinline__ uint32_t range_mask(int base, int lo, int hi)
 {
@@ -239,7 +239,10 @@ __device__ bool walk_ahead(const Params &p, const Tables &t, long long pos0, int
 // =====================================================================================================
 // Decoupled look-back (single chain, 16-byte aggregate records, LB_WINDOW predecessors per step)
 // =====================================================================================================
-constexpr int LB_PER_LANE = 8;
+#ifndef LATOK_LB_PER_LANE
+#define LATOK_LB_PER_LANE 2
+#endif
+constexpr int LB_PER_LANE = LATOK_LB_PER_LANE;
 constexpr int LB_WINDOW = 32 * LB_PER_LANE;
 
 __device__ __forceinline__ uint4 ld_rec(const void *p)
@@ -308,6 +311,9 @@ __device__ Prefix lookback(long long tile, const Params &p, int lane)
                     for (int j = 0; j < LB_PER_LANE; ++j)
                         if (first + j >= 0 && !((rec[j].x >> 2) == p.epoch && (rec[j].x & 3u) != 0u)) { rec[j] = ld_rec(p.agg + (first + j)); pending = true; }
                     if (!pending) break;
+#ifdef LATOK_PROFILE
+                    if (lane == 31) atomicAdd(&p.result->prof[14], 1ull);
+#endif
                     if (++spins > SPIN_LIMIT || (((spins & 1023u) == 0u) && ld_volatile_u32(&p.result->abort_flag))) {
                         atomicOr(&p.result->error, 1u);
                         st_volatile_u32(&p.result->abort_flag, 1u);
@@ -341,6 +347,9 @@ __device__ Prefix lookback(long long tile, const Params &p, int lane)
             }
             const unsigned has_reset = __ballot_sync(0xFFFFFFFFu, rj >= 0);
             const int Lr = has_reset ? 31 - __clz(has_reset) : -1;
+#ifdef LATOK_PROFILE
+            if (lane == 0) { atomicAdd(&p.result->prof[13], 1ull); if (Lr >= 0) atomicAdd(&p.result->prof[8], (unsigned long long)((31 - Lr) * LB_PER_LANE)); }
+#endif
             const bool contrib = lane >= Lr;          // lanes older than the newest inclusive element are superseded
             // characters / tokens
             const unsigned wn = __reduce_add_sync(0xFFFFFFFFu, contrib ? ln : 0u), wk = __reduce_add_sync(0xFFFFFFFFu, contrib ? lk : 0u);
@@ -913,6 +922,7 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
                 __syncthreads();
                 warp_seed = seed;
             }
+            PROF(10);
             // backlog after the last owned character (tile transfer function at 0) and at the end of ACT
             if (closed) { if (tid == NT - 1) { sc.v_tile = out; sc.x_end = out; } }
             else { if (tid == END_OWNED_THREAD - 1) sc.v_tile = out; if (tid == NT - 1) sc.x_end = out; }
@@ -992,6 +1002,7 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
 #pragma unroll
             for (int w = 0; w < NWARP; ++w) { const int t = scratch[96 + w]; if (w < warp) tp += t; ntok_tile += t; }
 
+            PROF(11);
             if (attempt == 1) break;
             // ================================================================ publish aggregate, look back
             if (warp == 0) {
@@ -1012,6 +1023,7 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
                 if (lane == 0) { sc.G_in = pre.G; sc.base_in = pre.base; sc.K_in = pre.K; sc.x_in = pre.x; }
             }
             __syncthreads();  // (G)
+            PROF(12);
             if (sc.x_in == 0) break;
             // a backlog does enter this tile (rare): redo the block mask with it
             x_tile_in = sc.x_in;
