@@ -1,0 +1,97 @@
+"""Full-size BASELINE configs on the GPU: size-independent invariants over the whole batch plus exact
+parity with the oracle on random samples of strings (the oracle needs seconds per 10 MB).  -m gpu."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from latok_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def check_invariants(buf, off, r, feats=False):
+    S = len(off) - 1
+    lead = ((buf & 0xC0) != 0x80).astype(np.int64)
+    cum = np.concatenate([[0], np.cumsum(lead)])
+    assert np.array_equal(r.char_offsets, cum[off]), "per-string character counts != UTF-8 lead-byte counts"
+    assert r.n_chars == int(cum[-1]) and len(r.splits) == r.n_chars
+    assert r.tok_offsets[0] == 0 and r.tok_offsets[-1] == r.n_tokens and np.all(np.diff(r.tok_offsets) >= 0)
+    L = np.diff(r.char_offsets)
+    nonempty = L > 0
+    assert np.all(r.splits[r.char_offsets[:-1][nonempty]] == 1), "first character of a string is always a boundary (=1)"
+    assert r.splits.min() >= 0 and r.splits.max() <= 5
+    # spans: inside their string, ordered, start on a split, end on a split or the string end, no split inside
+    sid = np.repeat(np.arange(S), np.diff(r.tok_offsets))
+    st, en = r.spans[:, 0].astype(np.int64), r.spans[:, 1].astype(np.int64)
+    assert np.all((0 <= st) & (st < en) & (en <= L[sid]))
+    same = sid[1:] == sid[:-1]
+    assert np.all(en[:-1][same] <= st[1:][same]), "tokens of a string are disjoint and ordered"
+    g0 = r.char_offsets[sid]
+    assert np.all(r.splits[g0 + st] != 0)
+    inner_end = en < L[sid]
+    assert np.all(r.splits[(g0 + en)[inner_end]] != 0)
+    nzc = np.concatenate([[0], np.cumsum(r.splits != 0)])
+    assert np.all(nzc[g0 + en] - nzc[g0 + st + 1] == 0), "a token contains no split point besides its first character"
+    if feats:
+        assert r.tok_feats.shape == (r.n_tokens, 25)
+        # ALPHA_NUM >= ALPHA, ALPHA_NUM >= NUM per token while nothing wraps (short tokens)
+        short = (en - st) < 120
+        assert np.all(r.tok_feats[short, 1] >= r.tok_feats[short, 0]) and np.all(r.tok_feats[short, 1] >= r.tok_feats[short, 2])
+
+
+def check_sample(buf, off, r, idx, feats=False):
+    from latok_b200 import synth
+    raw = buf.tobytes()
+    for i in idx:
+        t = raw[off[i]:off[i + 1]].decode("utf-8")
+        m = oracle.parse_matrix(t)
+        s = oracle.split_mask(m) if len(t) else np.zeros(0, np.int8)
+        assert np.array_equal(r.string_splits(i), s), f"string {i}: split mask"
+        sp, _ = oracle.spans(s, m)
+        assert np.array_equal(r.string_spans(i), sp), f"string {i}: spans"
+        if feats:
+            assert np.array_equal(r.string_feats(i), oracle.token_feats(m, sp)), f"string {i}: token features"
+
+
+def test_config2_one_million_tweets(engine):
+    from latok_b200 import synth
+    buf, off = synth.tweets(1_000_000)
+    r = engine.run_packed(buf, off, 1 | 2)
+    check_invariants(buf, off, r)
+    rng = np.random.default_rng(0)
+    check_sample(buf, off, r, rng.integers(0, 1_000_000, size=4000))
+    check_sample(buf, off, r, range(0, 300))
+    check_sample(buf, off, r, range(999_700, 1_000_000))
+    r2 = engine.run_packed(buf, off, 1 | 2)     # deterministic
+    assert np.array_equal(r.splits, r2.splits) and np.array_equal(r.spans, r2.spans)
+    # sharding property: two byte-balanced halves tokenized separately concatenate to the whole
+    from latok_b200 import sharding
+    halves = sharding.tokenize_sharded(buf, off, [0, 0])
+    assert np.array_equal(halves.splits, r.splits) and np.array_equal(halves.spans, r.spans)
+    assert np.array_equal(halves.tok_offsets, r.tok_offsets) and np.array_equal(halves.char_offsets, r.char_offsets)
+
+
+def test_config4_mixed_unicode_with_classification(engine):
+    from latok_b200 import synth
+    buf, off = synth.mixed_unicode(300_000)
+    r = engine.run_packed(buf, off, 1 | 2 | 4)
+    check_invariants(buf, off, r, feats=True)
+    rng = np.random.default_rng(1)
+    check_sample(buf, off, r, rng.integers(0, 300_000, size=2500), feats=True)
+
+
+def test_config3_long_documents(engine):
+    from latok_b200 import synth
+    buf, off = synth.long_docs(1500, 65536)      # ~100 MB of unique text, incl. >= 32 KB space-free runs and backlog chunks
+    r = engine.run_packed(buf, off, 1 | 2)
+    check_invariants(buf, off, r)
+    runs = [i for i in range(1500) if (buf[off[i]:off[i + 1]] == 0x2C).mean() > 0.05][:6]
+    check_sample(buf, off, r, list(range(0, 40)) + runs)
+    assert r.lookahead_walks >= 0

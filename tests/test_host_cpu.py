@@ -1,0 +1,174 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/*.h
+declares, argument validation works without a GPU (no compute calls), string packing, byte-balanced
+sharding, and the world_size-2 token-count exchange over gloo."""
+import ctypes as C
+import os
+import re
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import corpus
+from oracle import oracle
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_functions():
+    text = (ROOT / "include" / "latok_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"LATOK_B200_API\s+[\w\s\*]+?\b(latok_b200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from latok_b200 import _lib
+    L = _lib.load()
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/latok_b200.h but not exported"
+    assert L.latok_b200_abi_version() == 1
+
+
+def test_header_cites_the_reference_interface():
+    text = (ROOT / "include" / "latok_b200.h").read_text()
+    for cite in ("latok.c:373-378", "latok.c:31-138", "latok.c:140-258", "latok.c:275-370", "default_tokenizer.py:113-134"):
+        assert cite in text
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    from latok_b200 import _lib
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    from latok_b200.engine import Engine
+    with pytest.raises(_lib.LatokCudaError, match="no CPU fallback"):
+        Engine(0)
+    from latok_b200.core.default_tokenizer import tokenize
+    with pytest.raises(_lib.LatokCudaError):
+        list(tokenize("no gpu here"))
+
+
+def test_argument_validation_without_gpu():
+    from latok_b200 import _lib
+    L = _lib.load()
+    h = C.c_void_p()
+    assert L.latok_b200_create(0, 0, -1, C.byref(h)) == _lib.EINVAL
+    assert L.latok_b200_submit(None, None, None, 0, 3) == _lib.EINVAL
+    assert b"engine is NULL" in L.latok_b200_last_error()
+    assert L.latok_b200_fetch(None, None, None, None, None, None, None) == _lib.EINVAL
+    assert L.latok_b200_destroy(None) == _lib.OK
+
+
+def test_product_never_imports_the_oracle():
+    for path in (ROOT / "latok_b200").rglob("*"):
+        if path.suffix in (".py", ".cu", ".h", ".cuh") and "_gen" not in path.parts:
+            assert not re.search(r"import\s+oracle|from\s+oracle|from\s+\.+oracle|liblatok_oracle|oracle[/.](oracle|ref_driver|_ref|_build)",
+                                 path.read_text()), f"{path} reaches into oracle/"
+
+
+def test_pack_strings_roundtrip():
+    from latok_b200.engine import pack_strings
+    texts = corpus.FIXTURES + ["", "x", ""] + corpus.fuzz_strings(3, 200, 40)
+    buf, off = pack_strings(texts)
+    assert off[0] == 0 and off[-1] == len(buf) and np.all(np.diff(off) >= 0)
+    raw = buf.tobytes()
+    assert [raw[off[i]:off[i + 1]].decode("utf-8", "surrogatepass") for i in range(len(texts))] == texts
+
+
+def test_mirror_modules_match_reference_constants():
+    from latok_b200.core import offsets as oft
+    from latok_b200.core.latok_utils import FEATURE_NAMES, NUM_FEATURES, build_combo_matrix
+    assert oft.FEATURE_COUNT == NUM_FEATURES == 25 and oft.SPACE_IDX == 5 and oft.AFTER_NEXT_SLASH_IDX == 24
+    assert oft.CHAR_PERIOD_MASK == 0x80000 and oft.SPECIALS_MASK == 0x8000
+    assert FEATURE_NAMES[0] == "Alpha" and FEATURE_NAMES[24] == "After_Next_/" and FEATURE_NAMES[8] == "@"
+    m = build_combo_matrix([[1], [2, 3, 4], [5, 6]])
+    assert m.dtype == np.int8 and m.tolist() == [[1, -1, -1], [2, 3, 4], [5, 6, -1]]
+    assert np.array_equal(m, oracle.combo([[1], [2, 3, 4], [5, 6]]))
+
+
+def test_synthetic_corpora_are_valid_and_seeded():
+    from latok_b200 import synth
+    for fn, kw in ((synth.tweets, dict(n_strings=3000)), (synth.mixed_unicode, dict(n_strings=2000)),
+                   (synth.long_docs, dict(n_docs=6, doc_bytes=20000))):
+        b1, o1 = fn(**kw)
+        b2, o2 = fn(**kw)
+        assert np.array_equal(b1, b2) and np.array_equal(o1, o2)
+        assert o1[0] == 0 and o1[-1] == len(b1) and np.all(np.diff(o1) > 0)
+        b1.tobytes().decode("utf-8")   # well-formed
+    b, o = synth.tweets(3000)
+    lens = [len(s) for s in synth.to_strings(b, o)]
+    assert 100 < np.mean(lens) < 190
+
+
+def oracle_run(device, buf, offsets, what):
+    """Stand-in for an Engine on a box without GPUs: the oracle packaged as a BatchResult (test only)."""
+    from latok_b200.engine import BatchResult
+    o = oracle.tokenize_batch_utf8(buf, offsets, feats=bool(what & 4), matrix=bool(what & 8))
+    r = BatchResult(len(offsets) - 1, o["n_chars"], o["n_tokens"], splits=o["splits"], char_offsets=o["char_offsets"],
+                    spans=o["spans"], tok_offsets=o["tok_offsets"], tok_feats=o.get("tok_feats"), matrix=o.get("matrix"))
+    return r
+
+
+def test_shard_ranges_and_merge():
+    from latok_b200 import sharding, synth
+    buf, off = synth.tweets(5000, seed=7)
+    for g in (1, 2, 3, 4, 8):
+        rng = sharding.shard_ranges(off, g)
+        assert rng[0][0] == 0 and rng[-1][1] == len(off) - 1
+        assert all(a[1] == b[0] for a, b in zip(rng, rng[1:]))
+        sizes = [int(off[b] - off[a]) for a, b in rng]
+        assert max(sizes) - min(sizes) <= 2 * int(np.diff(off).max())      # byte balanced to within a string
+        merged = sharding.tokenize_sharded(buf, off, list(range(g)), what=1 | 2 | 4, run_fn=oracle_run)
+        whole = oracle_run(0, buf, off, 1 | 2 | 4)
+        for name in ("splits", "char_offsets", "spans", "tok_offsets", "tok_feats"):
+            assert np.array_equal(getattr(merged, name), getattr(whole, name)), (g, name)
+    # more shards than strings, empty strings, empty batch
+    tiny_b, tiny_o = np.frombuffer(b"ab cd", dtype=np.uint8), np.array([0, 2, 2, 5], dtype=np.int64)
+    m = sharding.tokenize_sharded(tiny_b, tiny_o, [0, 1, 2, 3, 4], run_fn=oracle_run)
+    w = oracle_run(0, tiny_b, tiny_o, 3)
+    assert np.array_equal(m.spans, w.spans) and np.array_equal(m.tok_offsets, w.tok_offsets)
+    assert sharding.shard_ranges(np.array([0], dtype=np.int64), 4) == [(0, 0)] * 4
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+    from latok_b200 import sharding, synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    buf, off = synth.tweets(2000, seed=11)
+    s0, s1 = sharding.shard_ranges(off, world)[rank]
+    b, o = sharding.slice_shard(buf, off, s0, s1)
+    r = oracle_run(rank, np.ascontiguousarray(b), np.ascontiguousarray(o), 3)
+    counts, cbase, tbase = sharding.allgather_counts(r.n_chars, r.n_tokens)
+    r = sharding.rebase_for_rank(r, cbase, tbase)
+    q.put((rank, s0, s1, counts.tolist(), r.char_offsets.tolist(), r.tok_offsets.tolist(), r.spans.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_count_exchange_over_gloo():
+    import torch.multiprocessing as mp
+    from latok_b200 import synth
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    buf, off = synth.tweets(2000, seed=11)
+    whole = oracle_run(0, buf, off, 3)
+    (r0, a0, b0, counts0, co0, to0, sp0), (r1, a1, b1, counts1, co1, to1, sp1) = got
+    assert counts0 == counts1 and a0 == 0 and b0 == a1 and b1 == 2000
+    assert co0[:-1] + co1 == whole.char_offsets.tolist()
+    assert to0[:-1] + to1 == whole.tok_offsets.tolist()
+    assert sp0 + sp1 == whole.spans.tolist()
