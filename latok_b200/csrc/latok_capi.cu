@@ -130,6 +130,7 @@ struct latok_b200_engine {
     DevBuf<AggRec> agg;
     DevBuf<IncRec> inc;
     DevBuf<OpenSums> osum;
+    DevBuf<unsigned long long> span_scratch;
     DevBuf<Result> d_result;
     PinBuf<uint8_t> h_in;
     PinBuf<long long> h_off;
@@ -267,7 +268,7 @@ int latok_b200_destroy(latok_b200_engine *e)
     e->d_table.release(); e->d_in.release(); e->d_scratch.release(); e->d_scratch2.release(); e->d_scratch3.release();
     e->d_off.release(); e->d_first.release(); e->d_char_off.release(); e->d_tok_off.release();
     e->d_splits.release(); e->d_feats.release(); e->d_matrix.release(); e->d_spans.release();
-    e->agg.release(); e->inc.release(); e->osum.release();
+    e->agg.release(); e->inc.release(); e->osum.release(); e->span_scratch.release();
     e->d_result.release();
     e->h_in.release(); e->h_off.release(); e->h_result.release();
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
@@ -333,13 +334,15 @@ static int run_device(latok_b200_engine *e)
     p.feats = e->d_feats.p; p.matrix = e->d_matrix.p;
     p.cap_tokens = (long long)(e->d_spans.cap / 2);
     p.what = e->what;
-    p.agg = e->agg.p; p.inc = e->inc.p; p.osum = e->osum.p; p.epoch = e->epoch;
+    p.agg = e->agg.p; p.inc = e->inc.p; p.osum = e->osum.p; p.span_scratch = e->span_scratch.p; p.epoch = e->epoch;
     p.ticket = &e->d_result.p->ticket; p.ticket_base = 0;
     p.result = e->d_result.p;
     p.table_blob = e->d_table.p; p.tl = e->tl; p.rules = e->rules;
     const bool words = (e->what & (LATOK_B200_FEATS | LATOK_B200_MATRIX)) != 0;
     int grid = e->n_sm * tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words);
     if ((long long)grid > ntiles) grid = (int)ntiles;
+    if (int r = e->span_scratch.ensure((size_t)grid * 2 * SPAN_SCRATCH)) return r;
+    p.span_scratch = e->span_scratch.p;
 
     CU(cudaMemsetAsync(e->d_result.p, 0, sizeof(Result), e->stream));
     CU(launch_tile_index(e->cur_off, e->n_strings, e->n_bytes, e->d_first.p, ntiles, e->d_result.p, e->stream));
@@ -425,6 +428,11 @@ int latok_b200_sizes(latok_b200_engine *e, int64_t *n_chars, int64_t *n_tokens)
         const Result res = *e->h_result.p;
         if (res.error & 2u) { e->submitted = false; return fail(LATOK_B200_EINVAL, "offsets must start at 0, be non-decreasing and end at the buffer length"); }
         if (res.error & 1u) { e->submitted = false; return fail(LATOK_B200_EINTERNAL, "device look-back watchdog tripped"); }
+        if (res.error & 8u) {
+            e->submitted = false;
+            return fail(LATOK_B200_EINTERNAL, "device consistency check failed: tile %llu G_in %llu K_in %llu n_own %lld ntok %lld c_lo %lld c_hi %lld",
+                        res.prof[8], res.prof[9], res.prof[10], (long long)res.prof[11], (long long)res.prof[12], (long long)res.prof[13], (long long)res.prof[14]);
+        }
         if ((res.error & 4u) || (long long)res.n_tokens > (long long)(e->d_spans.cap / 2)) {
             // token buffers too small: grow to the exact count and run the batch again
             const size_t need = (size_t)res.n_tokens + 1024;

@@ -22,6 +22,7 @@ constexpr int FIRST_OWNED_THREAD = LHALO / 32;
 constexpr int END_OWNED_THREAD = (LHALO + TILE) / 32;
 constexpr int LUT_ENTRIES = 272;        // 256 byte values (>= 0x80: no features) + 16 non-ASCII classes
 constexpr int SPAN_STAGE = 1536;        // tokens staged in shared memory per tile before the coalesced write
+constexpr int SPAN_SCRATCH = WINB + 64; // per CTA and slot: global stage for tiles with more tokens than that
 
 constexpr int NFEAT = 25;
 constexpr int MAX_RULE_ROWS = 15;
@@ -98,6 +99,7 @@ struct Params {
     AggRec *agg;
     IncRec *inc;
     OpenSums *osum;
+    void *span_scratch;   // int2 [grid][2][SPAN_SCRATCH]
     unsigned epoch;
     unsigned long long *ticket;
     unsigned long long ticket_base;

@@ -28,7 +28,7 @@ constexpr uint32_t FIRSTBIT = 1u << 25;   // character starts a string
 constexpr uint32_t LASTBIT = 1u << 26;    // character ends a string
 constexpr uint32_t FEATMASK = (1u << NFEAT) - 1;
 constexpr int NEG = -(1 << 28);           // "-infinity" of the (max,+) backlog functions
-constexpr unsigned SPIN_LIMIT = 1u << 27; // watchdog for look-back spins
+constexpr unsigned SPIN_LIMIT = 1u << 23; // watchdog for look-back spins
 
 // ---- small helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mask_lt(int k) { return __funnelshift_lc(0xFFFFFFFFu, 0u, (unsigned)max(k, 0)); }  // low k bits (k clamped to 0..32)
@@ -48,7 +48,7 @@ __device__ __forceinline__ Fn fn_compose(Fn f, Fn g)  // g after f
 __device__ __forceinline__ int fn_apply(Fn f, int x) { return max(x + f.u, f.v); }
 
 #ifdef LATOK_PROFILE
-#define PROF(i) do { if (threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&p.result->prof[i], (unsigned long long)(_t - _prof_t)); _prof_t = _t; } } while (0)
+#define PROF(i) do { if (threadIdx.x == 32) { long long _t = clock64(); atomicAdd(&p.result->prof[i], (unsigned long long)(_t - _prof_t)); _prof_t = _t; } } while (0)
 #else
 #define PROF(i) do { } while (0)
 #endif
@@ -248,12 +248,12 @@ constexpr int LB_WINDOW = 32 * LB_PER_LANE;
 __device__ __forceinline__ uint4 ld_rec(const void *p)
 {
     uint4 r;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void st_rec(void *p, uint4 v)
 {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 struct Prefix { unsigned long long G, base, K; int x; };
@@ -299,6 +299,9 @@ __device__ Prefix lookback(long long tile, const Params &p, int lane)
             int rj = -1;                              // newest inclusive element of this lane
             unsigned long long rG = 0, rB = 0, rK = 0; int rx = 0;
             unsigned ln = 0, lk = 0, llf = 0; bool lhas = false; long long lviol = -1; int lastv = 0;
+#ifdef LATOK_PROFILE
+            long long _lt0 = clock64();
+#endif
             // all records of this lane in flight at once; re-poll only the ones not yet published
             uint4 rec[LB_PER_LANE];
 #pragma unroll
@@ -322,6 +325,9 @@ __device__ Prefix lookback(long long tile, const Params &p, int lane)
                     }
                 }
             }
+#ifdef LATOK_PROFILE
+            if (lane == 31) { long long _t = clock64(); atomicAdd(&p.result->prof[6], (unsigned long long)(_t - _lt0)); _lt0 = _t; }
+#endif
             // the newest inclusive record of this lane: fetch its prefix
 #pragma unroll
             for (int j = 0; j < LB_PER_LANE; ++j) if (first + j >= 0 && (rec[j].x & 3u) == 2u) rj = j;
@@ -368,6 +374,9 @@ __device__ Prefix lookback(long long tile, const Params &p, int lane)
             if (vmin != 0x7FFFFFFF && viol < 0) viol = newest - vmin;
             if (!x_set) { x_in = __shfl_sync(0xFFFFFFFFu, lastv, 31); x_set = true; }
             if (!__all_sync(0xFFFFFFFFu, ok)) { out.x = 0; return out; }    // watchdog tripped: error flag is set
+#ifdef LATOK_PROFILE
+            if (lane == 31) { long long _t = clock64(); atomicAdd(&p.result->prof[7], (unsigned long long)(_t - _lt0)); }
+#endif
             if (Lr >= 0) {
                 const unsigned long long G0 = __shfl_sync(0xFFFFFFFFu, rG, Lr), B0 = __shfl_sync(0xFFFFFFFFu, rB, Lr);
                 const unsigned long long K0 = __shfl_sync(0xFFFFFFFFu, rK, Lr);
@@ -393,31 +402,58 @@ __device__ Prefix lookback(long long tile, const Params &p, int lane)
 }
 
 // =====================================================================================================
-// tokenize_kernel (v3): bit-planes in registers, one speculative look-back chain, chunk-aligned tiles
+// tokenize_kernel (v4): bit-planes in registers, one speculative look-back chain, chunk-aligned tiles,
+// warp-specialised: warp 0 = service warp (tile tickets, TMA loads, string-start maps, aggregate publish,
+// look-back), warps 1..8 = compute warps.  The compute warps stage a tile's outputs in shared memory, hand
+// its aggregate to the service warp and go on with the next tile; the outputs of tile k-1 are written once its
+// prefix has arrived, so the look-back latency is off the compute warps' critical path.
 // =====================================================================================================
 enum { PL_A = 0, PL_N = 1, PL_NUM = 2, PL_LO = 3, PL_UP = 4, PL_SP = 5, PL_SY = 6, PL_TW = 7, PL_AT = 8, PL_CO = 9,
        PL_SL = 10, PL_PE = 11 };
 constexpr int VPAD = 256;      // staging slack in front of the first owned character
-constexpr int SEARCH = RHALO - TRUST_MARGIN;   // bytes after a nominal tile boundary searched for a closer
+constexpr int NTS = 32;        // service warp
+constexpr int NTHREADS = NT + NTS;
+constexpr int NBUF = 3;        // window buffers: one being computed, one staged for output, one being loaded
+// named barriers (0 is __syncthreads, used during set-up only)
+enum { BAR_C = 1, BAR_AGG = 2, BAR_PRE = 4, BAR_LOADED = 6, BAR_FREE = 9 };
+
+__device__ __forceinline__ void nb_sync(int id, int cnt) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(cnt) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int cnt) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(cnt) : "memory"); }
+__device__ __forceinline__ int cbar_or(int pred)   // __syncthreads_or over the compute warps
+{
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.or.pred q, 1, 256, p;\n\tselp.s32 %0, 1, 0, q;\n\t}" : "=r"(r) : "r"(pred) : "memory");
+    return r;
+}
+#define CBAR() nb_sync(BAR_C, NT)
+
+struct Slot {            // per-tile state handed from the compute warps to the service warp and to the output stage
+    long long tile;
+    int c_lo, c_hi, n_own, ntok, last_tile;
+    int lft_rel;         // last owned string start relative to c_lo, or -1
+    int v_tile;          // backlog leaving the tile
+    int nbf;             // tokens counted before the first owned string start (their indices still lack G_in - base_in)
+    int end0, end0_rel;  // first split that ends the token left open by earlier tiles (-1: none); relative like above?
+    int span_global;     // spans staged in the global scratch (more tokens than the shared-memory stage holds)
+    unsigned long long G_in, base_in, K_in;   // mailbox, written by the service warp
+    int x_in, redo;
+};
 
 struct SmemPlan {
-    int mbar, scal, tile0, tile1, table, spans, startbits, leadmask, cpref, emit, tokpref, split, edge, scratch, words, total;
+    int mbar, scal, slots, tile[NBUF], table, spans[2], startbits, leadmask[2], cpref[2], emit[2], tokpref[2], split, edge, scratch, words, total;
 };
 __host__ __device__ inline SmemPlan smem_plan(int table_bytes, bool want_words)
 {
     SmemPlan s; int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
-    s.mbar = take(16);
+    s.mbar = take(32);
     s.scal = take(256);
-    s.tile0 = take(WINB + VPAD + 64);   // window bytes; re-used as the split-value staging buffer
-    s.tile1 = take(WINB + VPAD + 64);
+    s.slots = take(2 * (int)sizeof(Slot));
+    for (int b = 0; b < NBUF; ++b) s.tile[b] = take(WINB + VPAD + 64);   // window bytes; re-used as the split-value stage
     s.table = take(table_bytes);
-    s.spans = take(SPAN_STAGE * 8 + 16);
-    s.startbits = take(2 * NT * 4);
-    s.leadmask = take(NT * 4);
-    s.cpref = take((NT + 1) * 4);
-    s.emit = take(NT * 4);
-    s.tokpref = take((NT + 1) * 4);
+    for (int i = 0; i < 2; ++i) s.spans[i] = take(SPAN_STAGE * 8 + 16);
+    s.startbits = take(NBUF * NT * 4);
+    for (int i = 0; i < 2; ++i) { s.leadmask[i] = take(NT * 4); s.cpref[i] = take((NT + 1) * 4); s.emit[i] = take(NT * 4); s.tokpref[i] = take((NT + 1) * 4); }
     s.split = take(NT * 4);
     s.edge = take(NWARP * 16 * 4);
     s.scratch = take(1024);
@@ -428,16 +464,12 @@ __host__ __device__ inline SmemPlan smem_plan(int table_bytes, bool want_words)
 size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words) { return (size_t)smem_plan(tl.total, want_words).total; }
 
 struct Scalars {          // block-shared scalars
-    long long tile_q[2];
-    int tma_used[2];
-    unsigned long long G_in, base_in, K_in;
-    int x_in;
+    long long tile_id[NBUF];
+    int tma_used[NBUF];
     int c_lo, c_hi, lo_found, hi_found;
     int need_walk, far;
     int v_tile, x_end;
-    unsigned open_has;
-    unsigned open_sums[8];
-    unsigned carry_sums[8];
+    int end0, end0_rel, nbf;
 };
 
 // LUT entry (256 + class) of the multi-byte character whose lead byte is p[0] >= 0xC0
@@ -520,36 +552,137 @@ __device__ __forceinline__ int eval_backlog(int x, uint32_t Mm, uint32_t FmA, ui
     return x;
 }
 
+
 template <bool kDefault, bool kWords>
-__global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Params p)
+__global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(const Params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const SmemPlan sp = smem_plan(p.tl.total, kWords);
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.mbar);   // [2]
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.mbar);   // [NBUF]
     Scalars &sc = *reinterpret_cast<Scalars *>(smem + sp.scal);
+    Slot *slots = reinterpret_cast<Slot *>(smem + sp.slots);
     uint8_t *tableS = smem + sp.table;
-    int2 *spanS = reinterpret_cast<int2 *>(smem + sp.spans);
-    uint32_t *startbitsS = reinterpret_cast<uint32_t *>(smem + sp.startbits);   // [2][NT]
-    uint32_t *leadmaskS = reinterpret_cast<uint32_t *>(smem + sp.leadmask);
-    int *cprefS = reinterpret_cast<int *>(smem + sp.cpref);
-    uint32_t *emitS = reinterpret_cast<uint32_t *>(smem + sp.emit);
-    int *tokprefS = reinterpret_cast<int *>(smem + sp.tokpref);
+    uint32_t *startbitsS = reinterpret_cast<uint32_t *>(smem + sp.startbits);   // [NBUF][NT]
     uint32_t *splitS = reinterpret_cast<uint32_t *>(smem + sp.split);
     uint32_t *edgeS = reinterpret_cast<uint32_t *>(smem + sp.edge);
     int *scratch = reinterpret_cast<int *>(smem + sp.scratch);
     uint32_t *wordS = reinterpret_cast<uint32_t *>(smem + sp.words);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
     if (ld_volatile_u32(&p.result->error) & 2u) return;  // offsets failed validation in tile_index_kernel
 
     // one-time per CTA: tables into shared memory, mbarrier init, clean start-bit maps
-    for (int i = tid; i < p.tl.total / 16; i += NT)
+    for (int i = threadIdx.x; i < p.tl.total / 16; i += NTHREADS)
         reinterpret_cast<uint4 *>(tableS)[i] = __ldg(reinterpret_cast<const uint4 *>(p.table_blob) + i);
-    startbitsS[tid] = 0; startbitsS[NT + tid] = 0;
-    if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); sc.tile_q[0] = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base); }
+    for (int i = threadIdx.x; i < NBUF * NT; i += NTHREADS) startbitsS[i] = 0;
+    if (threadIdx.x == 0) { for (int b = 0; b < NBUF; ++b) mbar_init(mbar + b, 1); }
     __syncthreads();
+    const bool want_feats = (p.what & 4u) != 0u, want_matrix = (p.what & 8u) != 0u;
+    const bool want_spans = (p.what & 2u) != 0u, want_splits = (p.what & 1u) != 0u;
+    int2 *span_scratch = reinterpret_cast<int2 *>(p.span_scratch) + (size_t)blockIdx.x * 2 * SPAN_SCRATCH;
+
+    // =================================================================================================
+    // service warp
+    // =================================================================================================
+    if (threadIdx.x < NTS) {
+        const int lane = threadIdx.x;
+        // Start loading window `t` into buffer `b`: TMA bulk copy of the 16-byte aligned interior, plain loads for
+        // the ragged ends, and the string-start bitmap.
+        auto begin_load = [&](long long t, int b) {
+            uint8_t *tileS = smem + sp.tile[b];
+            const long long w0 = t * (long long)TILE - LHALO;
+            const long long lo = w0 < 0 ? 0 : w0;
+            long long hi = w0 + WINB;
+            const long long full16 = p.n_bytes & ~15LL;
+            if (hi > full16) hi = full16;
+            const int tma_bytes = hi > lo ? int(hi - lo) : 0;
+            if (lane == 0) {
+                sc.tma_used[b] = tma_bytes > 0;
+                if (tma_bytes > 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(mbar + b, (uint32_t)tma_bytes);
+                    tma_load_1d(tileS + (lo - w0), p.in + lo, (uint32_t)tma_bytes, mbar + b);
+                }
+            }
+            const int a_end = int(lo - w0);
+            const int b_beg = a_end + tma_bytes;
+            for (int i = lane; i < a_end; i += NTS) tileS[i] = 0;
+            for (int i = b_beg + lane; i < WINB + 16; i += NTS) {
+                const long long g = w0 + i;
+                tileS[i] = (g >= 0 && g < p.n_bytes) ? p.in[g] : (uint8_t)0;
+            }
+            uint32_t *sbm = startbitsS + b * NT;
+            const long long wend = w0 + WINB;
+            for (long long s = p.tile_first_str[t] + lane; s <= p.n_strings; s += NTS) {
+                const long long o = p.offsets[s];
+                if (o >= wend) break;
+                const int wb = int(o - w0);
+                atomicOr(&sbm[wb >> 5], 1u << (wb & 31));
+            }
+        };
+        auto fetch_and_load = [&](int b) {
+            long long t = 0;
+            if (lane == 0) t = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base);
+            t = __shfl_sync(FULL, t, 0);
+            if (lane == 0) sc.tile_id[b] = t;
+            if (t < p.ntiles) begin_load(t, b);
+            __syncwarp();
+            nb_arrive(BAR_LOADED + b, NTHREADS);
+            return t;
+        };
+        long long ids[NBUF];
+        ids[0] = fetch_and_load(0);
+        ids[1] = fetch_and_load(1);
+        ids[2] = 0;
+        for (int k = 0;; ++k) {
+            const int b = k % NBUF, s = k & 1;
+            const long long tile = b == 0 ? ids[0] : (b == 1 ? ids[1] : ids[2]);
+            if (tile >= p.ntiles) break;
+            nb_sync(BAR_AGG + s, NTHREADS);          // the compute warps have staged tile k and filled its slot
+            Slot &sl = slots[s];
+            const int n_own = sl.n_own, ntok = sl.ntok, lft_rel = sl.lft_rel, v_tile = sl.v_tile;
+            if (lane == 0) {
+                uint4 r;
+                r.x = (p.epoch << 2) | 1u;
+                r.y = (unsigned)n_own | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
+                r.z = (unsigned)ntok | ((unsigned)v_tile << 16);
+                r.w = 0;
+                st_rec(p.agg + tile, r);
+            }
+            const Prefix pre = lookback(tile, p, lane);
+            if (lane == 0) {
+                sl.G_in = pre.G; sl.base_in = pre.base; sl.K_in = pre.K; sl.x_in = pre.x; sl.redo = pre.x != 0;
+                if (pre.x == 0) {
+                    // inclusive prefix (a tile that does receive a backlog recomputes first and publishes it itself)
+                    IncRec *ir = p.inc + tile;
+                    uint4 a, bq;
+                    const unsigned long long Gn = pre.G + (unsigned long long)n_own, Kn = pre.K + (unsigned long long)ntok;
+                    const unsigned long long Bn = lft_rel >= 0 ? pre.G + (unsigned long long)lft_rel : pre.base;
+                    a.x = (unsigned)Gn; a.y = (unsigned)(Gn >> 32); a.z = (unsigned)Bn; a.w = (unsigned)(Bn >> 32);
+                    bq.x = (unsigned)Kn; bq.y = (unsigned)(Kn >> 32); bq.z = (unsigned)v_tile; bq.w = 0;
+                    st_rec(ir, a); st_rec(reinterpret_cast<uint4 *>(ir) + 1, bq);
+                    __threadfence();
+                    uint4 r;
+                    r.x = (p.epoch << 2) | 2u;
+                    r.y = (unsigned)n_own | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
+                    r.z = (unsigned)ntok | ((unsigned)v_tile << 16);
+                    r.w = 0;
+                    st_rec(p.agg + tile, r);
+                }
+            }
+            __syncwarp();
+            nb_arrive(BAR_PRE + s, NTHREADS);
+            if (k >= 1) nb_sync(BAR_FREE + (k - 1) % NBUF, NTHREADS);   // buffer of tile k-1 written out
+            const long long t2 = fetch_and_load((k + 2) % NBUF);
+            if ((k + 2) % NBUF == 0) ids[0] = t2; else if ((k + 2) % NBUF == 1) ids[1] = t2; else ids[2] = t2;
+        }
+        return;
+    }
+
+    // =================================================================================================
+    // compute warps
+    // =================================================================================================
+    const int tid = threadIdx.x - NTS, lane = tid & 31, warp = tid >> 5;
     Tables tb;
     tb.ascii_feat = reinterpret_cast<const uint16_t *>(tableS + p.tl.ascii_feat);
     tb.class_feat = reinterpret_cast<const uint16_t *>(tableS + p.tl.class_feat);
@@ -559,67 +692,159 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
     const uint32_t *lut0 = reinterpret_cast<const uint32_t *>(tableS + p.tl.lut3);
     const uint32_t *lut1 = lut0 + LUT_ENTRIES, *lut2 = lut1 + LUT_ENTRIES;
     const uint32_t *lutv = reinterpret_cast<const uint32_t *>(tableS + p.tl.lutv);
-
 #ifdef LATOK_PROFILE
     long long _prof_t = clock64();
 #endif
     uint32_t phase_bits = 0;   // mbarrier phase per buffer
-    const bool want_feats = (p.what & 4u) != 0u, want_matrix = (p.what & 8u) != 0u;
-    const bool want_spans = (p.what & 2u) != 0u, want_splits = (p.what & 1u) != 0u;
 
-    // Start loading window `t` into buffer `b`: TMA bulk copy of the 16-byte aligned interior, plain loads for
-    // the ragged ends, and the string-start bitmap.  Called by all threads.
-    auto begin_load = [&](long long t, int b) {
-        uint8_t *tileS = smem + (b ? sp.tile1 : sp.tile0);
-        const long long w0 = t * (long long)TILE - LHALO;
-        const long long lo = w0 < 0 ? 0 : w0;
-        long long hi = w0 + WINB;
-        const long long full16 = p.n_bytes & ~15LL;
-        if (hi > full16) hi = full16;
-        const int tma_bytes = hi > lo ? int(hi - lo) : 0;
-        if (tid == 0) {
-            sc.tma_used[b] = tma_bytes > 0;
-            if (tma_bytes > 0) {
-                fence_proxy_async();
-                mbar_expect_tx(mbar + b, (uint32_t)tma_bytes);
-                tma_load_1d(tileS + (lo - w0), p.in + lo, (uint32_t)tma_bytes, mbar + b);
+    // ---- output stage: everything comes from the slot and the staged shared-memory state of that tile
+    auto emit = [&](int s, int b) {
+        const Slot &sl = slots[s];
+        const long long tile = sl.tile;
+        const long long w0 = tile * (long long)TILE - LHALO;
+        const int c_lo = sl.c_lo, c_hi = sl.c_hi, n_own = sl.n_own, ntok_tile = sl.ntok;
+        const bool last_tile = sl.last_tile != 0;
+        const unsigned long long G_in = sl.G_in, K_in = sl.K_in;
+        const int D = (int)(long long)(G_in - sl.base_in);    // characters of the open string before this tile
+        const uint8_t *valS = smem + sp.tile[b];
+        const uint32_t *leadmaskS = reinterpret_cast<const uint32_t *>(smem + sp.leadmask[s]);
+        const int *cprefS = reinterpret_cast<const int *>(smem + sp.cpref[s]);
+        const uint32_t *emitS = reinterpret_cast<const uint32_t *>(smem + sp.emit[s]);
+        const int *tokprefS = reinterpret_cast<const int *>(smem + sp.tokpref[s]);
+        if (K_in + (unsigned long long)ntok_tile > (unsigned long long)p.cap_tokens && tid == 0) atomicOr(&p.result->error, 4u);
+        // consistency check: a prefix can never exceed the input size (catches chain corruption instead of faulting)
+        if (G_in + (unsigned long long)n_own > (unsigned long long)p.n_bytes || K_in + (unsigned long long)ntok_tile > (unsigned long long)p.n_bytes ||
+            n_own < 0 || ntok_tile < 0) {
+            if (tid == 0 && atomicOr(&p.result->error, 8u) == 0u) {
+                p.result->prof[8] = (unsigned long long)tile; p.result->prof[9] = G_in; p.result->prof[10] = K_in;
+                p.result->prof[11] = (unsigned long long)(long long)n_own; p.result->prof[12] = (unsigned long long)(long long)ntok_tile;
+                p.result->prof[13] = (unsigned long long)(long long)c_lo; p.result->prof[14] = (unsigned long long)(long long)c_hi;
+            }
+            return;
+        }
+        if (want_splits && n_own > 0) {
+            // dst[j] <-> valS[VPAD + j]; 16-byte global chunks are assembled from the (differently aligned) staging words
+            int8_t *dst = p.splits + G_in;
+            const int a16 = int(G_in & 15ull);
+            const int head = (16 - a16) & 15;
+            const int nh = head < n_own ? head : n_own;
+            if (tid < nh) dst[tid] = (int8_t)valS[VPAD + tid];
+            const int nchunks = (n_own - nh) >> 4;
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(valS);
+            const int sbyte = VPAD + nh;                    // staging byte of chunk 0
+            const int shb = 8 * (sbyte & 3);
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + nh);
+            for (int i = tid; i < nchunks; i += NT) {
+                const uint32_t *q = sw + ((sbyte + 16 * i) >> 2);
+                uint4 v;
+                if (shb == 0) { v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3]; }
+                else {
+                    const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+                    v.x = __funnelshift_r(q0, q1, shb); v.y = __funnelshift_r(q1, q2, shb);
+                    v.z = __funnelshift_r(q2, q3, shb); v.w = __funnelshift_r(q3, q4, shb);
+                }
+                d4[i] = v;
+            }
+            const int done = nh + (nchunks << 4);
+            if (tid < n_own - done) dst[done + tid] = (int8_t)valS[VPAD + done + tid];
+        }
+        if (want_spans) {
+            const int2 *src = sl.span_global ? span_scratch + (size_t)s * SPAN_SCRATCH : reinterpret_cast<const int2 *>(smem + sp.spans[s]) + 1;
+            const int nbf = sl.nbf;
+            int2 *dst = reinterpret_cast<int2 *>(p.spans) + K_in;
+            for (int i = tid; i < ntok_tile; i += NT) {
+                int2 v = src[i];
+                if (i < nbf) { v.x += D; if (v.y >= 0) v.y += D; }
+                if ((long long)K_in + i < p.cap_tokens) {
+                    if (v.y >= 0) dst[i] = v;
+                    else p.spans[2 * (K_in + i)] = v.x;        // still open: a later tile writes the end
+                }
+            }
+            if (tid == 0 && sl.end0 >= 0) {
+                const long long k = (long long)K_in - 1;
+                if (k >= 0 && k < p.cap_tokens) p.spans[2 * k + 1] = sl.end0 + (sl.end0_rel ? D : 0);
             }
         }
-        const int a_end = int(lo - w0);
-        const int b_beg = a_end + tma_bytes;
-        for (int i = tid; i < a_end; i += NT) tileS[i] = 0;
-        for (int i = b_beg + tid; i < WINB + 16; i += NT) {
-            const long long g = w0 + i;
-            tileS[i] = (g >= 0 && g < p.n_bytes) ? p.in[g] : (uint8_t)0;
+        if (kWords && want_matrix) {
+            int8_t *dst = p.matrix + G_in * NFEAT;
+            const int nb = n_own * NFEAT;
+            for (int j = tid; j < nb; j += NT) {
+                const int c = j / NFEAT, f = j - c * NFEAT;
+                dst[j] = (int8_t)((wordS[widx(c_lo + c)] >> f) & 1u);
+            }
         }
-        uint32_t *sbm = startbitsS + b * NT;
-        const long long wend = w0 + WINB;
-        for (long long s = p.tile_first_str[t] + tid; s <= p.n_strings; s += NT) {
-            const long long o = p.offsets[s];
-            if (o >= wend) break;
-            const int wb = int(o - w0);
-            atomicOr(&sbm[wb >> 5], 1u << (wb & 31));
+        // per-string CSR offsets for the strings whose first character position is owned by this tile
+        {
+            auto cidx = [&](int wb) -> int {
+                int t = wb >> 5;
+                if (t >= NT) return cprefS[NT];
+                return cprefS[t] + __popc(leadmaskS[t] & mask_lt(wb & 31));
+            };
+            const long long wend = w0 + WINB;
+            for (long long q = p.tile_first_str[tile] + tid; q <= p.n_strings; q += NT) {
+                const long long o = p.offsets[q];
+                if (o >= wend) break;
+                const int wb = int(o - w0);
+                const int c = cidx(wb);
+                const bool mine = last_tile ? (c >= c_lo) : (c >= c_lo && c < c_hi);
+                if (!mine) continue;
+                p.char_off[q] = (long long)(G_in + (unsigned long long)(c - c_lo));
+                const int t = wb >> 5;
+                p.tok_off[q] = (long long)K_in + tokprefS[t] + __popc(emitS[t] & mask_lt(c - cprefS[t]));
+            }
+        }
+        if (last_tile && tid == 0) {
+            p.result->n_chars = G_in + (unsigned long long)n_own;
+            p.result->n_tokens = K_in + (unsigned long long)ntok_tile;
         }
     };
-    if (sc.tile_q[0] < p.ntiles) begin_load(sc.tile_q[0], 0);
 
-    for (int it = 0;; ++it) {
-        const int cur = it & 1;
-        PROF(9);
-        if (tid == 0) sc.tile_q[cur ^ 1] = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base);
-        __syncthreads();  // (A) previous tile completely done; loads/bitmap of this tile issued before are visible
-        const long long tile = sc.tile_q[cur];
-        if (tile >= p.ntiles) break;
-        const long long next_tile = sc.tile_q[cur ^ 1];
-        if (next_tile < p.ntiles) begin_load(next_tile, cur ^ 1);    // prefetch
-        if (sc.tma_used[cur]) { mbar_wait(mbar + cur, (phase_bits >> cur) & 1u); phase_bits ^= 1u << cur; }
-        PROF(0);
-
-        uint8_t *tileS = smem + (cur ? sp.tile1 : sp.tile0);
+    int k = 0, redo_k = -1;
+    bool drained = false;
+    for (;;) {
+        const bool is_redo = redo_k >= 0;
+        const int wk = is_redo ? redo_k : k;
+        const int bcur = wk % NBUF, scur = wk & 1;
+        uint8_t *tileS = smem + sp.tile[bcur];
         uint8_t *valS = tileS;            // the window bytes are dead after phase 1
-        uint32_t *sbm = startbitsS + cur * NT;
+        uint32_t *sbm = startbitsS + bcur * NT;
+        uint32_t *leadmaskS = reinterpret_cast<uint32_t *>(smem + sp.leadmask[scur]);
+        int *cprefS = reinterpret_cast<int *>(smem + sp.cpref[scur]);
+        uint32_t *emitS = reinterpret_cast<uint32_t *>(smem + sp.emit[scur]);
+        int *tokprefS = reinterpret_cast<int *>(smem + sp.tokpref[scur]);
+        int2 *spanS = reinterpret_cast<int2 *>(smem + sp.spans[scur]);
+        long long tile = 0;
+        int x_tile_in = 0;
+        bool have_work = true;
+        PROF(9);
+        if (is_redo) {
+            // a backlog does enter this tile (rare): fetch its window again and recompute with it
+            tile = slots[scur].tile; x_tile_in = slots[scur].x_in;
+            const long long w0r = tile * (long long)TILE - LHALO;
+            for (int i = tid; i < WINB + 16; i += NT) {
+                const long long g = w0r + i;
+                tileS[i] = (g >= 0 && g < p.n_bytes) ? p.in[g] : (uint8_t)0;
+            }
+            sbm[tid] = 0;
+            CBAR();
+            const long long wend = w0r + WINB;
+            for (long long q = p.tile_first_str[tile] + tid; q <= p.n_strings; q += NT) {
+                const long long o = p.offsets[q];
+                if (o >= wend) break;
+                const int wb = int(o - w0r);
+                atomicOr(&sbm[wb >> 5], 1u << (wb & 31));
+            }
+            CBAR();
+        } else {
+            nb_sync(BAR_LOADED + bcur, NTHREADS);
+            tile = sc.tile_id[bcur];
+            if (tile >= p.ntiles) have_work = false;
+            else if (sc.tma_used[bcur]) { mbar_wait(mbar + bcur, (phase_bits >> bcur) & 1u); phase_bits ^= 1u << bcur; }
+        }
+        PROF(0);
+        if (have_work) {
         const long long w0 = tile * (long long)TILE - LHALO;
-        if (tid == 0) { sc.need_walk = 0; sc.far = 0; sc.open_has = 0; sc.lo_found = 0; sc.hi_found = 0; }
+        if (tid == 0) { sc.need_walk = 0; sc.far = 0; sc.lo_found = 0; sc.hi_found = 0; sc.end0 = -1; sc.end0_rel = 0; sc.nbf = -1; }
 
         // ------------------------------------------------------------------ phase 1: bytes -> bit-planes
         const int wb0 = tid * 32;
@@ -716,7 +941,7 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
         }
         if (lane == 31) { edgeS[warp * 16 + 8] = myLB; scratch[warp] = nscan; }
         leadmaskS[tid] = lead;
-        __syncthreads();  // (B)
+        CBAR();  // (B)
         int c0 = nscan - n, c_end = 0;
 #pragma unroll
         for (int w = 0; w < NWARP; ++w) { const int t = scratch[w]; if (w < warp) c0 += t; c_end += t; }
@@ -830,7 +1055,7 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
             for (int j = 0; j < 32; ++j)
                 if (j < n) wordS[widx(c0 + j)] = a[j];
         }
-        __syncthreads();  // (C) boundaries
+        CBAR();  // (C) boundaries
         PROF(2);
 
         auto cidx = [&](int wb) -> int {  // characters starting at window bytes < wb
@@ -897,11 +1122,9 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
             uint4 *o = reinterpret_cast<uint4 *>(p.osum + tile);
             st_rec(o, a); st_rec(o + 1, b); st_rec(o + 2, c4);
         };
-        // ------------------------------------------------------------------ phase 2b/3 (speculative: no backlog enters)
         uint32_t HOT = 0, Zm = 0, SPLIT = 0, E = 0, V[5];
         int ntok_tile = 0, tp = 0, slow = 0;
-        int x_tile_in = 0;
-        for (int attempt = 0;; ++attempt) {
+        {
             // ---- backlog relaxation: every thread starts from 0, carries are propagated until nothing changes
             int xin = 0, out = 0, warp_seed = warp == 0 ? x_tile_in : 0, pub = 0;
             if (Mm) out = eval_backlog(0, Mm, FmA, S, Lm, HOT); else HOT = 0;
@@ -917,12 +1140,11 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
                 const bool ch = o31 != pub;
                 pub = o31;
                 if (lane == 31) scratch[64 + warp] = o31;
-                if (!__syncthreads_or(ch ? 1 : 0)) break;   // (D)
+                if (!cbar_or(ch ? 1 : 0)) break;   // (D)
                 const int seed = warp > 0 ? scratch[64 + warp - 1] : x_tile_in;
-                __syncthreads();
+                CBAR();
                 warp_seed = seed;
             }
-            PROF(10);
             // backlog after the last owned character (tile transfer function at 0) and at the end of ACT
             if (closed) { if (tid == NT - 1) { sc.v_tile = out; sc.x_end = out; } }
             else { if (tid == END_OWNED_THREAD - 1) sc.v_tile = out; if (tid == NT - 1) sc.x_end = out; }
@@ -951,7 +1173,7 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
                         if (nr > 0 && ((CL >> (nr - 1)) & 1u) == 0u && above == 0u) sc.need_walk = 1;
                     }
                 }
-                __syncthreads();  // (E)
+                CBAR();  // (E)
                 const unsigned above = lane == 31 ? 0u : (H & (0xFFFFFFFFu << (lane + 1)));
                 if (above) cin = (FH >> (__ffs(above) - 1)) & 1u;
                 else {
@@ -964,9 +1186,9 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
                 if (sc.x_end >= 1) { if (tid == 0) sc.far = 1; }
                 else if (warp == 0) {
                     bool any = walk_ahead(p, tb, w0 + WINB - TRUST_MARGIN, lane);
-                    if (lane == 0) { sc.far = any ? 1 : 0; if (attempt == 0) atomicAdd(&p.result->walks, 1ull); }
+                    if (lane == 0) { sc.far = any ? 1 : 0; if (!is_redo) atomicAdd(&p.result->walks, 1ull); }
                 }
-                __syncthreads();
+                CBAR();
             }
             if (cin == 1 || (cin == 2 && sc.far)) {
                 const uint32_t top = hasCL ? ~((2u << (31 - __clz(CL))) - 1u) : 0xFFFFFFFFu;
@@ -997,38 +1219,11 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
             for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, tscan, d); if (lane >= d) tscan += t; }
             if (lane == 31) scratch[96 + warp] = tscan;
             emitS[tid] = E; splitS[tid] = SPLIT;
-            slow = __syncthreads_or((want_splits && nvalid == 32 && n < 4) ? 1 : 0);  // (F) malformed UTF-8 only
+            slow = cbar_or((want_splits && nvalid == 32 && n < 4) ? 1 : 0);  // (F) malformed UTF-8 only
             tp = tscan - mytok; ntok_tile = 0;
 #pragma unroll
             for (int w = 0; w < NWARP; ++w) { const int t = scratch[96 + w]; if (w < warp) tp += t; ntok_tile += t; }
 
-            PROF(11);
-            if (attempt == 1) break;
-            // ================================================================ publish aggregate, look back
-            if (warp == 0) {
-                int lft = -1, cm = 0, cs = 0;
-#pragma unroll
-                for (int w = 0; w < NWARP; ++w) { lft = max(lft, scratch[128 + w]); cm += scratch[144 + w]; cs += scratch[152 + w]; }
-                const int v_tile = sc.v_tile;
-                if (lane == 0) {
-                    uint4 r;
-                    r.x = (p.epoch << 2) | 1u;
-                    r.y = (unsigned)n_own | ((lft >= 0 ? (unsigned)(lft - c_lo + 1) : 0u) << 16);
-                    r.z = (unsigned)ntok_tile | ((unsigned)v_tile << 16);
-                    r.w = (unsigned)(lft >= 0 ? NEG : cm - cs);
-                    if (kWords && want_feats) { publish_open_sums(); __threadfence(); }
-                    st_rec(p.agg + tile, r);
-                }
-                const Prefix pre = lookback(tile, p, lane);
-                if (lane == 0) { sc.G_in = pre.G; sc.base_in = pre.base; sc.K_in = pre.K; sc.x_in = pre.x; }
-            }
-            __syncthreads();  // (G)
-            PROF(12);
-            if (sc.x_in == 0) break;
-            // a backlog does enter this tile (rare): redo the block mask with it
-            x_tile_in = sc.x_in;
-            if (tid == 0) { sc.need_walk = 0; sc.far = 0; }
-            __syncthreads();
         }
         PROF(3);
         {   // latest owned string start in the warps before this one
@@ -1037,58 +1232,39 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
             for (int w = 0; w < NWARP; ++w) if (w < warp) lfw = max(lfw, scratch[128 + w]);
             lf_excl = max(lf_excl, lfw);
         }
-        const unsigned long long G_in = sc.G_in, K_in = sc.K_in;
-        // publish the inclusive prefix
-        if (tid == 0) {
-            int lft = -1;
+        int lft = -1, ffirst = 0x7FFFFFFF;
 #pragma unroll
-            for (int w = 0; w < NWARP; ++w) lft = max(lft, scratch[128 + w]);
-            if (kWords && want_feats && x_tile_in != 0) publish_open_sums();
-            IncRec *ir = p.inc + tile;
-            uint4 a, b;
-            const unsigned long long Gn = G_in + (unsigned long long)n_own, Kn = K_in + (unsigned long long)ntok_tile;
-            const unsigned long long Bn = lft >= 0 ? G_in + (unsigned long long)(lft - c_lo) : sc.base_in;
-            a.x = (unsigned)Gn; a.y = (unsigned)(Gn >> 32); a.z = (unsigned)Bn; a.w = (unsigned)(Bn >> 32);
-            b.x = (unsigned)Kn; b.y = (unsigned)(Kn >> 32); b.z = (unsigned)sc.v_tile; b.w = 0;
-            st_rec(ir, a); st_rec(reinterpret_cast<uint4 *>(ir) + 1, b);
-            __threadfence();
-            uint4 r = ld_rec(p.agg + tile);
-            r.x = (p.epoch << 2) | 2u;
-            st_rec(p.agg + tile, r);
-        }
+        for (int w = 0; w < NWARP; ++w) { lft = max(lft, scratch[128 + w]); ffirst = min(ffirst, scratch[136 + w]); }
 
-        // ------------------------------------------------------------------ phase 4: staging
+        // ------------------------------------------------------------------ phase 4: staging (no prefix needed)
         tokprefS[tid] = tp;
         if (tid == 0) tokprefS[NT] = ntok_tile;
-        // string-relative index = tile character index - cbase; for the string that began before this tile
-        // cbase = -(characters of it before the tile) - c_lo ... folded in as `delta` below
-        const long long delta_ll = (long long)(G_in - sc.base_in) - (long long)c_lo;     // idx = c + delta
-        const int delta = (int)delta_ll;
-        const bool stage_ok = ntok_tile <= SPAN_STAGE - 1 && K_in + (unsigned long long)ntok_tile <= (unsigned long long)p.cap_tokens;
-        if (K_in + (unsigned long long)ntok_tile > (unsigned long long)p.cap_tokens && tid == 0) atomicOr(&p.result->error, 4u);
+        const bool span_global = ntok_tile > SPAN_STAGE - 1;
+        // tokens counted before the first owned string start belong to the string that began in an earlier tile:
+        // their indices are staged relative to c_lo and get (G_in - base_in) added when they are written out
+        if (ffirst != 0x7FFFFFFF && c0 <= ffirst && ffirst < c0 + n) sc.nbf = tp + __popc(E & mask_lt(ffirst - c0));
         if (want_spans) {
-            // one (start, end) pair per token; end = next split (a string start is always a split)
-            // first split of each following thread, for tokens that run past this thread's characters
+            // one (start, end) pair per token; end = next split (a string start is always a split).
             // splits that may end a token of this tile: owned ones, plus (closed range) the string start right after it
             const uint32_t SPq = SPLIT & mask_lt(n) & range_mask(c0, c_lo, closed ? c_hi + 1 : c_hi);
             const int myfirst = SPq ? c0 + __ffs(SPq) - 1 : -1;
+            const unsigned hs = __ballot_sync(FULL, myfirst >= 0);
             {
-                const unsigned hs = __ballot_sync(FULL, myfirst >= 0);
                 const int wf = __shfl_sync(FULL, myfirst, hs ? __ffs(hs) - 1 : 0);
                 if (lane == 0) scratch[160 + warp] = hs ? wf : -1;
             }
-            __syncthreads();  // (H)
+            CBAR();  // (H)
             int nextsplit;     // tile index of the first split in the following threads (-1: none in this window)
             {
-                const unsigned hs = __ballot_sync(FULL, myfirst >= 0);
                 const unsigned above = lane == 31 ? 0u : (hs & (0xFFFFFFFFu << (lane + 1)));
                 const int got = __shfl_sync(FULL, myfirst, above ? __ffs(above) - 1 : 0);
                 nextsplit = above ? got : -1;
                 if (!above) for (int w2 = warp + 1; w2 < NWARP; ++w2) if (scratch[160 + w2] >= 0) { nextsplit = scratch[160 + w2]; break; }
             }
+            int2 *stage = span_global ? span_scratch + (size_t)scur * SPAN_SCRATCH : spanS + 1;
             uint32_t ev = E;
             int rank = 0;
-            int cbase = lf_excl >= 0 ? lf_excl : -delta;     // idx = c - cbase
+            int cbase = lf_excl >= 0 ? lf_excl : c_lo;       // idx = c - cbase (relative to c_lo until a string starts)
             while (ev) {
                 const int i = __ffs(ev) - 1; ev &= ev - 1;
                 const uint32_t fb = Fm & OWN & mask_lt(i + 1);
@@ -1097,12 +1273,7 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
                 const int endc = ab ? c0 + __ffs(ab) - 1 : nextsplit;
                 const int sidx = c0 + i - (((SPLIT >> i) & 1u) ? 0 : 1) - cbase;
                 const int eidx = endc >= 0 ? endc - cbase : -1;
-                const int lord = tp + rank;
-                if (stage_ok) spanS[1 + lord] = make_int2(sidx, eidx);
-                else {
-                    const long long k = (long long)K_in + lord;
-                    if (k < p.cap_tokens) { p.spans[2 * k] = sidx; if (eidx >= 0) p.spans[2 * k + 1] = eidx; }
-                }
+                stage[tp + rank] = make_int2(sidx, eidx);
                 ++rank;
             }
             // the first split of the tile that follows a non-space character ends the token left open by earlier tiles
@@ -1114,9 +1285,9 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
                     const int i = __ffs(END) - 1;
                     if (tp + __popc(E & mask_lt(i)) == 0) {
                         const uint32_t fb = Fm & OWN & mask_lt(i);      // string starts strictly before the split
-                        const int cb = fb ? c0 + 31 - __clz(fb) : (lf_excl >= 0 ? lf_excl : -delta);
-                        const long long k = (long long)K_in - 1;
-                        if (k >= 0 && k < p.cap_tokens) p.spans[2 * k + 1] = c0 + i - cb;
+                        const bool rel = !fb && lf_excl < 0;
+                        const int cb = fb ? c0 + 31 - __clz(fb) : (lf_excl >= 0 ? lf_excl : c_lo);
+                        sc.end0 = c0 + i - cb; sc.end0_rel = rel ? 1 : 0;
                     }
                 }
             }
@@ -1153,7 +1324,7 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
             }
             uint32_t headw = __shfl_up_sync(FULL, tailw, 1);
             if (lane == 31) edgeS[warp * 16 + 9] = tailw;
-            __syncthreads();  // (I0)
+            CBAR();  // (I0)
             if (lane == 0) headw = warp > 0 ? edgeS[(warp - 1) * 16 + 9] : 0u;
             const int o = VPAD + c0 - c_lo;                 // staging offset of this thread's first character
             if (tid >= FIRST_OWNED_THREAD && o >= 4 && n > 0) {
@@ -1190,8 +1361,25 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
                 }
             }
         }
-        __syncthreads();  // (I) staging complete
+        if (kWords && want_feats && tid == 0) { publish_open_sums(); __threadfence(); }
+        if (tid == 0) {
+            Slot &sl = slots[scur];
+            sl.tile = tile; sl.c_lo = c_lo; sl.c_hi = c_hi; sl.n_own = n_own; sl.ntok = ntok_tile; sl.last_tile = last_tile ? 1 : 0;
+            sl.lft_rel = lft >= 0 ? lft - c_lo : -1;
+            sl.span_global = span_global ? 1 : 0;
+        }
+        CBAR();  // (I) staging complete; sc.* final
+        if (tid == 0) {
+            Slot &sl = slots[scur];
+            sl.v_tile = sc.v_tile; sl.nbf = sc.nbf >= 0 ? sc.nbf : ntok_tile; sl.end0 = sc.end0; sl.end0_rel = sc.end0_rel;
+        }
         PROF(4);
+        if (kWords && want_feats) {
+            // token-feature mode writes its rows with the prefix in hand (this mode is not pipelined)
+            if (!is_redo) { nb_arrive(BAR_AGG + scur, NTHREADS); nb_sync(BAR_PRE + scur, NTHREADS); }
+            const bool need_redo = !is_redo && slots[scur].redo != 0;
+            if (!need_redo) {
+                const unsigned long long K_in = slots[scur].K_in;
         if (kWords && want_feats) {
             // every split that follows a non-space character ends a token: sum the feature words back to its start
             const uint32_t PSr = (Sraw << 1) | ((LB >> 3) & 1u);
@@ -1215,69 +1403,48 @@ __global__ void __launch_bounds__(NT, kWords ? 1 : 2) tokenize_kernel(const Para
             }
         }
 
-        // ------------------------------------------------------------------ phase 5: coalesced output
-        if (want_splits && n_own > 0) {
-            // dst[j] <-> valS[VPAD + j]; 16-byte global chunks are assembled from the (differently aligned) staging words
-            int8_t *dst = p.splits + G_in;
-            const int a16 = int(G_in & 15ull);
-            const int head = (16 - a16) & 15;
-            const int nh = head < n_own ? head : n_own;
-            if (tid < nh) dst[tid] = (int8_t)valS[VPAD + tid];
-            const int nchunks = (n_own - nh) >> 4;
-            const uint32_t *sw = reinterpret_cast<const uint32_t *>(valS);
-            const int sbyte = VPAD + nh;                    // staging byte of chunk 0
-            const int shb = 8 * (sbyte & 3);
-            uint4 *d4 = reinterpret_cast<uint4 *>(dst + nh);
-            for (int i = tid; i < nchunks; i += NT) {
-                const uint32_t *q = sw + ((sbyte + 16 * i) >> 2);
-                uint4 v;
-                if (shb == 0) { v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3]; }
-                else {
-                    const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
-                    v.x = __funnelshift_r(q0, q1, shb); v.y = __funnelshift_r(q1, q2, shb);
-                    v.z = __funnelshift_r(q2, q3, shb); v.w = __funnelshift_r(q3, q4, shb);
-                }
-                d4[i] = v;
-            }
-            const int done = nh + (nchunks << 4);
-            if (tid < n_own - done) dst[done + tid] = (int8_t)valS[VPAD + done + tid];
-        }
-        if (want_spans && stage_ok) {
-            int2 *dst = reinterpret_cast<int2 *>(p.spans) + K_in;
-            for (int i = tid; i < ntok_tile; i += NT) {
-                int2 v = spanS[1 + i];
-                if (v.y >= 0) dst[i] = v;
-                else p.spans[2 * (K_in + i)] = v.x;
             }
         }
-        if (kWords && want_matrix) {
-            int8_t *dst = p.matrix + G_in * NFEAT;
-            const int nb = n_own * NFEAT;
-            for (int j = tid; j < nb; j += NT) {
-                const int c = j / NFEAT, f = j - c * NFEAT;
-                dst[j] = (int8_t)((wordS[widx(c_lo + c)] >> f) & 1u);
+        }  // have_work
+
+        if (is_redo) {
+            // publish the exact inclusive prefix of the recomputed tile, then write it out
+            if (tid == 0) {
+                Slot &sl = slots[scur];
+                IncRec *ir = p.inc + sl.tile;
+                uint4 a, bq;
+                const unsigned long long Gn = sl.G_in + (unsigned long long)sl.n_own, Kn = sl.K_in + (unsigned long long)sl.ntok;
+                const unsigned long long Bn = sl.lft_rel >= 0 ? sl.G_in + (unsigned long long)sl.lft_rel : sl.base_in;
+                a.x = (unsigned)Gn; a.y = (unsigned)(Gn >> 32); a.z = (unsigned)Bn; a.w = (unsigned)(Bn >> 32);
+                bq.x = (unsigned)Kn; bq.y = (unsigned)(Kn >> 32); bq.z = (unsigned)sl.v_tile; bq.w = 0;
+                st_rec(ir, a); st_rec(reinterpret_cast<uint4 *>(ir) + 1, bq);
+                __threadfence();
+                uint4 r = ld_rec(p.agg + sl.tile);
+                r.x = (p.epoch << 2) | 2u;
+                st_rec(p.agg + sl.tile, r);
             }
+            emit(scur, bcur);
+            CBAR();
+            nb_arrive(BAR_FREE + bcur, NTHREADS);
+            redo_k = -1;
+            if (drained) break;
+            continue;
         }
-        // per-string CSR offsets for the strings whose first character position is owned by this tile
-        {
-            const long long wend = w0 + WINB;
-            for (long long s = p.tile_first_str[tile] + tid; s <= p.n_strings; s += NT) {
-                const long long o = p.offsets[s];
-                if (o >= wend) break;
-                const int wb = int(o - w0);
-                const int c = cidx(wb);
-                const bool mine = last_tile ? (c >= c_lo) : (c >= c_lo && c < c_hi);
-                if (!mine && !(tile == 0 && c < c_lo)) continue;
-                p.char_off[s] = (long long)(G_in + (unsigned long long)(c - c_lo));
-                const int t = wb >> 5;
-                p.tok_off[s] = (long long)K_in + tokprefS[t] + __popc(emitS[t] & mask_lt(c - cprefS[t]));
-            }
-        }
-        if (last_tile && tid == 0) {
-            p.result->n_chars = G_in + (unsigned long long)n_own;
-            p.result->n_tokens = K_in + (unsigned long long)ntok_tile;
+        int j;   // tile whose outputs are written now
+        if (have_work) {
+            if (!(kWords && want_feats)) nb_arrive(BAR_AGG + scur, NTHREADS);
+            j = kWords ? k : k - 1;
+            ++k;
+        } else { j = kWords ? -1 : k - 1; drained = true; }
+        if (j >= 0) {
+            if (!(kWords && want_feats)) nb_sync(BAR_PRE + (j & 1), NTHREADS);
+            if (slots[j & 1].redo) { redo_k = j; continue; }
+            emit(j & 1, j % NBUF);
+            CBAR();
+            nb_arrive(BAR_FREE + j % NBUF, NTHREADS);
         }
         PROF(5);
+        if (drained) break;
     }
 }
 
@@ -1291,7 +1458,7 @@ static cudaError_t launch_one(const Params &p, int grid, cudaStream_t s)
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    tokenize_kernel<kDefault, kWords><<<grid, NT, smem, s>>>(p);
+    tokenize_kernel<kDefault, kWords><<<grid, NTHREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -1300,10 +1467,10 @@ int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words
     int nb = 0;
     const size_t smem = tokenize_smem_bytes(tl, want_words);
     cudaError_t e;
-    if (is_default && !want_words) { cudaFuncSetAttribute(tokenize_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<true, false>, NT, smem); }
-    else if (is_default) { cudaFuncSetAttribute(tokenize_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<true, true>, NT, smem); }
-    else if (!want_words) { cudaFuncSetAttribute(tokenize_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<false, false>, NT, smem); }
-    else { cudaFuncSetAttribute(tokenize_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<false, true>, NT, smem); }
+    if (is_default && !want_words) { cudaFuncSetAttribute(tokenize_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<true, false>, NTHREADS, smem); }
+    else if (is_default) { cudaFuncSetAttribute(tokenize_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<true, true>, NTHREADS, smem); }
+    else if (!want_words) { cudaFuncSetAttribute(tokenize_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<false, false>, NTHREADS, smem); }
+    else { cudaFuncSetAttribute(tokenize_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<false, true>, NTHREADS, smem); }
     if (e != cudaSuccess) { cudaGetLastError(); return 1; }
     return nb < 1 ? 1 : nb;
 }
