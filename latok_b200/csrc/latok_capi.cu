@@ -308,8 +308,14 @@ int latok_b200_set_rules(latok_b200_engine *e, const int8_t *split, int sr, int 
 
 static int run_device(latok_b200_engine *e)
 {
-    const long long ntiles = e->n_bytes / TILE + 1;
-    if (int r = e->d_first.ensure((size_t)ntiles + 1)) return r;
+    // token-feature / matrix modes run the v4 kernel (one CTA per 7 936-byte tile); split mask + spans run v5 (one warp
+    // per 3 968-byte range, V5_NW ranges per tile)
+    const bool words = (e->what & (LATOK_B200_FEATS | LATOK_B200_MATRIX)) != 0;
+    const bool use5 = !words && !getenv("LATOK_B200_FORCE_V4");
+    const int unit = use5 ? V5_RANGE : TILE;
+    const long long nunits = e->n_bytes / unit + 1;
+    const long long ntiles = use5 ? (nunits + V5_NW - 1) / V5_NW : nunits;
+    if (int r = e->d_first.ensure((size_t)nunits + 1)) return r;
     // the status word of every aggregate record carries the launch epoch, so records are zeroed only when (re)allocated
     if ((size_t)ntiles > e->agg.cap) { if (int r = e->agg.ensure((size_t)ntiles, true)) return r; }
     if (int r = e->inc.ensure((size_t)ntiles)) return r;
@@ -329,7 +335,7 @@ static int run_device(latok_b200_engine *e)
     Params p;
     memset(&p, 0, sizeof p);
     p.in = e->cur_in; p.n_bytes = e->n_bytes; p.offsets = e->cur_off; p.n_strings = e->n_strings;
-    p.tile_first_str = e->d_first.p; p.ntiles = ntiles;
+    p.tile_first_str = e->d_first.p; p.ntiles = ntiles; p.nranges = nunits;
     p.splits = e->d_splits.p; p.char_off = e->d_char_off.p; p.spans = e->d_spans.p; p.tok_off = e->d_tok_off.p;
     p.feats = e->d_feats.p; p.matrix = e->d_matrix.p;
     p.cap_tokens = (long long)(e->d_spans.cap / 2);
@@ -338,16 +344,16 @@ static int run_device(latok_b200_engine *e)
     p.ticket = &e->d_result.p->ticket; p.ticket_base = 0;
     p.result = e->d_result.p;
     p.table_blob = e->d_table.p; p.tl = e->tl; p.rules = e->rules;
-    const bool words = (e->what & (LATOK_B200_FEATS | LATOK_B200_MATRIX)) != 0;
-    int grid = e->n_sm * tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words);
+    int grid = e->n_sm * (use5 ? tokenize5_ctas_per_sm(e->tl, e->rules.is_default != 0)
+                               : tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words));
     if ((long long)grid > ntiles) grid = (int)ntiles;
-    if (int r = e->span_scratch.ensure((size_t)grid * 2 * SPAN_SCRATCH)) return r;
+    if (!use5) { if (int r = e->span_scratch.ensure((size_t)grid * 2 * SPAN_SCRATCH)) return r; }
     p.span_scratch = e->span_scratch.p;
 
     CU(cudaMemsetAsync(e->d_result.p, 0, sizeof(Result), e->stream));
-    CU(launch_tile_index(e->cur_off, e->n_strings, e->n_bytes, e->d_first.p, ntiles, e->d_result.p, e->stream));
+    CU(launch_tile_index(e->cur_off, e->n_strings, e->n_bytes, e->d_first.p, nunits, unit, e->d_result.p, e->stream));
     CU(cudaEventRecord(e->ev_k0, e->stream));
-    CU(launch_tokenize(p, grid, e->stream));
+    CU(use5 ? launch_tokenize5(p, grid, e->stream) : launch_tokenize(p, grid, e->stream));
     CU(cudaEventRecord(e->ev_k1, e->stream));
     CU(cudaMemcpyAsync(e->h_result.p, e->d_result.p, sizeof(Result), cudaMemcpyDeviceToHost, e->stream));
     e->launches += 2;

@@ -24,6 +24,13 @@ constexpr int LUT_ENTRIES = 272;        // 256 byte values (>= 0x80: no features
 constexpr int SPAN_STAGE = 1536;        // tokens staged in shared memory per tile before the coalesced write
 constexpr int SPAN_SCRATCH = WINB + 64; // per CTA and slot: global stage for tiles with more tokens than that
 
+// v5 kernel (latok_tok5.cu): one warp analyses a "range" (V5_RS steps of 1 KB, the last V5_HALO bytes shared with the
+// next range), a tile is the V5_NW ranges of one CTA
+constexpr int V5_RS = 4;
+constexpr int V5_HALO = 128;
+constexpr int V5_RANGE = V5_RS * 1024 - V5_HALO;
+constexpr int V5_NW = 8;
+
 constexpr int NFEAT = 25;
 constexpr int MAX_RULE_ROWS = 15;
 
@@ -88,6 +95,7 @@ struct Params {
     long long n_strings;
     const long long *tile_first_str;  // [ntiles + 1]
     long long ntiles;
+    long long nranges;                // v5: tile_first_str is indexed by range, ntiles counts groups of V5_NW ranges
     int8_t *splits;
     long long *char_off;
     int32_t *spans;
@@ -111,8 +119,10 @@ struct Params {
 
 size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words);
 int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words);
+int tokenize5_ctas_per_sm(const TableLayout &tl, bool is_default);
+cudaError_t launch_tokenize5(const Params &p, int grid, cudaStream_t s);
 cudaError_t launch_tile_index(const long long *offsets, long long n_strings, long long n_bytes,
-                              long long *tile_first_str, long long ntiles, Result *result, cudaStream_t s);
+                              long long *tile_first_str, long long ntiles, int tile_bytes, Result *result, cudaStream_t s);
 cudaError_t launch_tokenize(const Params &p, int grid, cudaStream_t s);
 cudaError_t launch_block_mask(const int8_t *a1, long long s1, const int8_t *a2, long long s2, long long n,
                               int8_t *out, unsigned char *scratch, cudaStream_t s);

@@ -1,0 +1,1023 @@
+// latok_tok5.cu -- tokenize kernel v5 (split mask + token spans + CSR offsets) for sm_100a.
+//
+// Work decomposition
+//   range  = what ONE WARP analyses on its own: a 4 KB window of the flat UTF-8 buffer, of which it owns the
+//            characters from just after the first chunk closer (space / end of string) found in the first 116
+//            bytes up to and including the first closer found in the 116 bytes after byte 3968.  Neighbouring
+//            ranges look at the same bytes and agree, so (almost) no block-mask state crosses a range boundary.
+//   step   = 1 KB of a range: lane l holds bytes [32l, 32l+32) as bit-planes (32 characters per register).
+//   tile   = the 8 consecutive ranges of one CTA; one decoupled look-back record per tile (service warp).
+//
+// Per range (compute warp, no CTA-wide barrier anywhere on this path):
+//   pass A  forward over the steps, software-pipelined (base planes of step j+1, then context + rules of step j):
+//           byte -> bit-plane transpose, bit-sliced ASCII classification, class-table patch for multi-byte
+//           characters, squeeze to character space, prev/next/after-next context (latok.c:68-73,99-134), rule
+//           sums (latok.c:318-341), and the block mask's forward half as a carry-propagating add
+//           (latok.c:218-244 when no chunk holds two marks; otherwise the whole tile is re-done by the exact
+//           mark-by-mark evaluation, pass B)
+//   pass C  backward over the steps: blank the chunks whose closer is hot, split values
+//           (default_tokenizer.py:121-132), token flags (default_tokenizer.py:148-158), counts
+//   -> the service warp sums the 8 ranges, publishes the tile aggregate, looks back, hands the prefix down
+//   pass D  forward: split bytes and (start,end) pairs staged per step in shared memory and written with
+//           aligned 16-byte stores; CSR offsets by one lane per string.
+//
+// No tensor cores: nothing here is a dense contraction; the bound is HBM bandwidth.
+#include "latok_device.cuh"
+
+namespace latok {
+namespace v5 {
+
+constexpr int NW = V5_NW;                  // compute warps per CTA (the service warp is warp NW)
+constexpr int NTH = (NW + 1) * 32;
+constexpr int RS = V5_RS;                // steps per range
+constexpr int STEP = 1024;
+constexpr int WIN = RS * STEP;
+constexpr int HALO = V5_HALO;
+constexpr int HLANES = HALO / 32;
+constexpr int RANGE = V5_RANGE;
+constexpr int MARGIN = 12;               // characters starting in the last 12 window bytes lack forward context
+constexpr int LPAD = 16;                 // bytes in front of the window (previous character)
+constexpr int XBYTES = LPAD + WIN + 16;
+constexpr int SPAD = 160;                // slack in front of the first owned character in the split stage
+constexpr int SSTAGE = SPAD + 16 + STEP + 48;
+constexpr int TCAP = 256;                // tokens staged per step; steps with more write their pairs directly
+constexpr int TSTAGE = (TCAP + 2) * 8;
+constexpr int SW = 7;                    // state words per lane and step handed from pass C to pass D: V0 V1 V2 E F lead packed
+enum { BAR_AGG = 1, BAR_PRE = 3 };
+static_assert(RANGE == WIN - HALO && HALO % 32 == 0 && RANGE % 16 == 0, "geometry");
+
+struct WAgg { int n_own, ntok, lft, v, flags, pad[3]; };
+struct Slot { unsigned long long G, K, base; int mode, x_in; };
+struct Ctl {
+    long long tile_id[2];
+    Slot slot[2];
+    WAgg wagg[2][NW];
+    int xch[NW + 1];
+    unsigned xgen[NW + 1];
+    int tokstep[NW][RS];                 // tokens per step
+    int nsa[NW][RS];                     // first split after the step (range-relative character index, -1: none)
+};
+
+struct Plan {
+    int tables, ctl, mbar, warp0, x, sst, tst, sbm, state, temp, per_warp, total;
+};
+__host__ __device__ inline Plan plan(const TableLayout &tl, bool is_default)
+{
+    Plan s; int o = 0;
+    auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
+    s.tables = take(tl.total - tl.lutv);
+    s.ctl = take((int)sizeof(Ctl));
+    s.mbar = take(8 * NW);
+    s.warp0 = o;
+    s.x = take(XBYTES);
+    s.sst = take(SSTAGE);
+    s.tst = take(TSTAGE);
+    s.sbm = take(RS * 32 * 4);
+    s.state = take(RS * SW * 32 * 4);
+    s.temp = is_default ? s.x + LPAD : take(RS * 16 * 32 * 4);   // default rules: 8 words per lane-word, in place of the input
+    s.per_warp = o - s.warp0;
+    s.total = s.warp0 + NW * s.per_warp;
+    return s;
+}
+
+#ifdef LATOK_PROFILE
+#define PROF5(i) do { if (lane == 0) { long long _t = clock64(); atomicAdd(&p.result->prof[i], (unsigned long long)(_t - _prof_t)); _prof_t = _t; } } while (0)
+#else
+#define PROF5(i) do { } while (0)
+#endif
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int CINF = 0x3FFFFFFF;
+
+// packed per-lane-word scalars: chars n (6 bits) | first char index c0 (13) << 6 | tokens before (11) << 19 | prev-is-space << 30
+__device__ __forceinline__ uint32_t pack_ncp(int n, int c0, int ps) { return (uint32_t)n | ((uint32_t)c0 << 6) | ((uint32_t)ps << 30); }
+__device__ __forceinline__ int pk_n(uint32_t k) { return (int)(k & 63u); }
+__device__ __forceinline__ int pk_c0(uint32_t k) { return (int)((k >> 6) & 8191u); }
+__device__ __forceinline__ int pk_tp(uint32_t k) { return (int)((k >> 19) & 2047u); }
+__device__ __forceinline__ uint32_t pk_ps(uint32_t k) { return (k >> 30) & 1u; }
+
+__device__ __forceinline__ int ld_vs32(const int *p) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p))); return v; }
+__device__ __forceinline__ void st_vs32(int *p, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
+
+template <bool kDefault>
+__global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const Params p)
+{
+    constexpr int NC = kDefault ? 3 : 4;      // split-count planes
+    constexpr int NY = kDefault ? 1 : 4;      // sym-count planes
+    constexpr int NV = kDefault ? 3 : 5;      // split-value planes
+    constexpr int TWD = kDefault ? 8 : 16;    // temp words per lane-word between pass A and pass C
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Plan sp = plan(p.tl, kDefault);
+    uint8_t *tableS = smem + sp.tables;
+    Ctl &ctl = *reinterpret_cast<Ctl *>(smem + sp.ctl);
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.mbar);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (ld_volatile_u32(&p.result->error) & 2u) return;  // offsets failed validation in tile_index_kernel
+
+    // ---- one-time per CTA: tables into shared memory, barriers, clean maps, first ticket
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.table_blob + p.tl.lutv);
+        const int n16 = (p.tl.total - p.tl.lutv) / 16;
+        for (int i = threadIdx.x; i < n16; i += NTH) reinterpret_cast<uint4 *>(tableS)[i] = __ldg(src + i);
+        for (int w = 0; w < NW; ++w) {
+            uint32_t *sbm = reinterpret_cast<uint32_t *>(smem + sp.warp0 + w * sp.per_warp + (sp.sbm - sp.warp0));
+            for (int i = threadIdx.x; i < RS * 32; i += NTH) sbm[i] = 0;
+        }
+        if (threadIdx.x == 0) {
+            for (int w = 0; w < NW; ++w) mbar_init(mbar + w, 1);
+            for (int w = 0; w <= NW; ++w) { ctl.xch[w] = 0; ctl.xgen[w] = 0; }
+            ctl.tile_id[0] = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base);
+        }
+    }
+    __syncthreads();
+    const bool want_spans = (p.what & 2u) != 0u, want_splits = (p.what & 1u) != 0u;
+
+    // =================================================================================================
+    // service warp: tickets, tile aggregate, look-back, prefix hand-down
+    // =================================================================================================
+    if (warp == NW) {
+        unsigned round = 0;
+        long long tile = ctl.tile_id[0];
+        for (int k = 0; tile < p.ntiles; ++k) {
+            const int s = k & 1;
+            long long tnext = 0;
+            if (lane == 0) { tnext = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base); ctl.tile_id[s ^ 1] = tnext; }
+            tnext = __shfl_sync(FULL, tnext, 0);
+            int n = 0, ntok = 0, lft_rel = -1, v = 0; bool irregular = false;
+            auto gather = [&]() {
+                nb_sync(BAR_AGG + s, NTH);
+                const WAgg a = ctl.wagg[s][lane < NW ? lane : 0];
+                const int mn = lane < NW ? a.n_own : 0, mk = lane < NW ? a.ntok : 0;
+                int pn = mn;                                   // inclusive prefix of characters over the ranges
+#pragma unroll
+                for (int d = 1; d < NW; d <<= 1) { const int t = __shfl_up_sync(FULL, pn, d); if (lane >= d) pn += t; }
+                n = __shfl_sync(FULL, pn, NW - 1);
+                ntok = __reduce_add_sync(FULL, mk);
+                const unsigned hl = __ballot_sync(FULL, lane < NW && a.lft >= 0);
+                const int src = hl ? 31 - __clz(hl) : 0;
+                const int lv = __shfl_sync(FULL, pn - mn + a.lft, src);
+                lft_rel = hl ? lv : -1;
+                v = __shfl_sync(FULL, a.v, NW - 1);
+                irregular = __any_sync(FULL, lane < NW && (a.flags & 1));
+            };
+            auto order_exact = [&](int x_in) {
+                ++round;
+                if (lane == 0) {
+                    ctl.slot[s].mode = 1; ctl.slot[s].x_in = x_in;
+                    st_vs32(&ctl.xch[0], x_in);
+                    __threadfence_block();
+                    st_vs32(reinterpret_cast<int *>(&ctl.xgen[0]), (int)round);
+                    __threadfence_block();
+                }
+                __syncwarp();
+                nb_arrive(BAR_PRE + s, NTH);
+            };
+            gather();
+            if (irregular) { order_exact(0); gather(); if (lane == 0) atomicAdd(&p.result->prof[15], 1ull); }
+            const unsigned ylf = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
+            if (lane == 0) {
+                uint4 r;
+                r.x = (p.epoch << 2) | 1u; r.y = ylf; r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
+                st_rec(p.agg + tile, r);
+            }
+            const Prefix pre = lookback(tile, p, lane);
+            if (pre.x != 0) { order_exact(pre.x); gather(); }
+            if (lane == 0) {
+                IncRec *ir = p.inc + tile;
+                uint4 a, bq;
+                const unsigned long long Gn = pre.G + (unsigned long long)n, Kn = pre.K + (unsigned long long)ntok;
+                const unsigned long long Bn = lft_rel >= 0 ? pre.G + (unsigned long long)lft_rel : pre.base;
+                a.x = (unsigned)Gn; a.y = (unsigned)(Gn >> 32); a.z = (unsigned)Bn; a.w = (unsigned)(Bn >> 32);
+                bq.x = (unsigned)Kn; bq.y = (unsigned)(Kn >> 32); bq.z = (unsigned)v; bq.w = 0;
+                st_rec(ir, a); st_rec(reinterpret_cast<uint4 *>(ir) + 1, bq);
+                __threadfence();
+                uint4 r;
+                r.x = (p.epoch << 2) | 2u;
+                r.y = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
+                r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
+                st_rec(p.agg + tile, r);
+                Slot &sl = ctl.slot[s];
+                sl.G = pre.G; sl.K = pre.K; sl.base = pre.base; sl.mode = 0; sl.x_in = 0;
+                __threadfence_block();
+            }
+            __syncwarp();
+            nb_arrive(BAR_PRE + s, NTH);
+            tile = tnext;
+        }
+        return;
+    }
+
+    // =================================================================================================
+    // compute warps
+    // =================================================================================================
+    unsigned char *wbase = smem + sp.warp0 + warp * sp.per_warp;
+    uint8_t *X = wbase + (sp.x - sp.warp0);
+    uint8_t *sst = wbase + (sp.sst - sp.warp0);
+    int2 *tst = reinterpret_cast<int2 *>(wbase + (sp.tst - sp.warp0));
+    uint32_t *sbmS = reinterpret_cast<uint32_t *>(wbase + (sp.sbm - sp.warp0));
+    uint32_t *stateS = reinterpret_cast<uint32_t *>(wbase + (sp.state - sp.warp0));
+    uint32_t *tempS = reinterpret_cast<uint32_t *>(wbase + (sp.temp - sp.warp0));
+    Tables tb;
+    tb.ascii_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.ascii_feat - p.tl.lutv));
+    tb.class_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.class_feat - p.tl.lutv));
+    tb.stage1 = tableS + (p.tl.stage1 - p.tl.lutv);
+    tb.stage2 = tableS + (p.tl.stage2 - p.tl.lutv);
+    tb.low_limit = p.tl.low_limit; tb.high_first = p.tl.high_first; tb.high_last = p.tl.high_last; tb.high_feat = p.tl.high_feat;
+    const uint32_t *lutv = reinterpret_cast<const uint32_t *>(tableS);
+#ifdef LATOK_PROFILE
+    long long _prof_t = clock64();
+#endif
+
+    // ---- window load: TMA bulk copy of the 16-byte aligned interior, plain loads for the ragged end
+    auto begin_load = [&](long long r) -> bool {
+        if (r >= p.nranges) return false;
+        const long long wl = r * (long long)RANGE - LPAD;          // global position of X[0]
+        const long long lo = wl < 0 ? 0 : wl;
+        long long hi = wl + XBYTES;
+        const long long full16 = p.n_bytes & ~15LL;
+        if (hi > full16) hi = full16;
+        const int tma_bytes = hi > lo ? int(hi - lo) : 0;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && tma_bytes > 0) {
+            mbar_expect_tx(mbar + warp, (uint32_t)tma_bytes);
+            tma_load_1d(X + (lo - wl), p.in + lo, (uint32_t)tma_bytes, mbar + warp);
+        }
+        const int a_end = int(lo - wl), b_beg = a_end + tma_bytes;
+        for (int i = lane; i < a_end; i += 32) X[i] = 0;
+        for (int i = b_beg + lane; i < XBYTES; i += 32) {
+            const long long g = wl + i;
+            X[i] = g < p.n_bytes ? p.in[g] : (uint8_t)0;
+        }
+        return tma_bytes > 0;
+    };
+    auto plain_load = [&](long long r) {          // exact re-analysis: fetch the window again
+        const long long wl = r * (long long)RANGE - LPAD;
+        for (int i = lane * 16; i < XBYTES; i += 512) {
+            const long long g = wl + i;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (g >= 0 && g + 16 <= p.n_bytes) v = *reinterpret_cast<const uint4 *>(p.in + g);
+            else if (g + 16 > 0 && g < p.n_bytes) {
+                uint8_t b[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) b[q] = (g + q >= 0 && g + q < p.n_bytes) ? p.in[g + q] : (uint8_t)0;
+                v.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+                v.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+                v.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
+                v.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
+            }
+            *reinterpret_cast<uint4 *>(X + i) = v;
+        }
+        __syncwarp();
+    };
+
+    // per-range results of the analysis
+    int c_lo = 0, c_hi = 0, n_own = 0, ntok_range = 0, lft = -1, v_out = 0, far = 0;
+    bool closed = true, lo_found = true, irregular = false, last_range = false, have = false;
+    long long w0 = 0, r = 0;
+
+    // ================================================================================================= analysis
+    auto analyze = [&](bool exact, unsigned round) {
+        c_lo = 0; c_hi = CINF; n_own = 0; ntok_range = 0; lft = -1; v_out = 0; far = 0;
+        closed = true; lo_found = true; irregular = false;
+        if (!have) {
+            if (exact) {      // pass the backlog on
+                int x = 0;
+                if (lane == 0) {
+                    unsigned spins = 0;
+                    while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xgen[warp])) != round) { if (++spins > (1u << 26)) break; }
+                    x = ld_vs32(&ctl.xch[warp]);
+                    st_vs32(&ctl.xch[warp + 1], x);
+                    __threadfence_block();
+                    st_vs32(reinterpret_cast<int *>(&ctl.xgen[warp + 1]), (int)round);
+                }
+                v_out = __shfl_sync(FULL, x, 0);
+            }
+            return;
+        }
+        // ---- string-start map of the window (bit = byte position), from the offsets of the strings that begin in it
+        {
+            const long long wend = w0 + WIN;
+            for (long long s = p.tile_first_str[r] + lane; s <= p.n_strings; s += 32) {
+                const long long o = p.offsets[s];
+                if (o >= wend) break;
+                const int wb = int(o - w0);
+                atomicOr(&sbmS[wb >> 5], 1u << (wb & 31));
+            }
+            __syncwarp();
+        }
+        // ---- the character in front of the window (prev-context of the first character)
+        uint32_t prevLB = 0;
+        if (w0 > 0) {
+            const uint8_t *q = X + LPAD - 1;
+            int back = 0;
+            while (back < 3 && (q[-back] & 0xC0u) == 0x80u) ++back;
+            const uint32_t w = classify_at(q - back, tb);
+            prevLB = (w & 1u) | (((w >> 1) & 1u) << 1) | (((w >> 3) & 1u) << 2) | (((w >> 5) & 1u) << 3) | (((w >> 6) & 1u) << 4);
+        }
+        const bool term_in_win = p.n_bytes < w0 + WIN;
+        const int jt = last_range ? int((p.n_bytes - w0) >> 10) : -1;       // step / lane / bit of the end of the data
+        const int lt = last_range ? int(((p.n_bytes - w0) >> 5) & 31) : 0, bt = last_range ? int((p.n_bytes - w0) & 31) : 0;
+
+        // pipeline registers: base planes of the step that awaits its context
+        uint32_t Pp[NBASE], Fp = 0, leadp = 0; int np = 0, c0p = 0;
+#pragma unroll
+        for (int f = 0; f < NBASE; ++f) Pp[f] = 0;
+        int crun = 0;                    // characters of the range so far
+        uint32_t pend = 0;               // fast block mask: a mark is pending in the open chunk
+        uint32_t dup_any = 0;
+
+#pragma unroll 1
+        for (int j = 0; j <= RS; ++j) {
+            // -------------------------------------------------------------- base planes of step j
+            uint32_t Pc[NBASE], Fc = 0, leadc = 0; int nc = 0, c0c = 0;
+#pragma unroll
+            for (int f = 0; f < NBASE; ++f) Pc[f] = 0;
+            if (j < RS) {
+                const uint8_t *src = X + LPAD + j * STEP + lane * 32;
+                const uint4 q0 = *reinterpret_cast<const uint4 *>(src), q1 = *reinterpret_cast<const uint4 *>(src + 16);
+                const uint32_t wds[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                uint32_t b[8];
+                bytes_to_planes(wds, b);
+                const long long g0 = w0 + j * STEP + lane * 32;
+                const long long rem = p.n_bytes - g0;
+                const int vhi = rem <= 0 ? 0 : (rem >= 32 ? 32 : int(rem));
+                const uint32_t valid = mask_lt(vhi);
+                const uint32_t sb = sbmS[j * 32 + lane];
+                sbmS[j * 32 + lane] = 0;
+                leadc = (~(b[7] & ~b[6]) & valid) | sb;
+                uint32_t mm = b[7] & b[6] & valid;                      // lead bytes of multi-byte characters
+                classify_ascii(b, Pc);
+                while (mm) {
+                    const int k = __ffs(mm) - 1; mm &= mm - 1;
+                    const uint32_t e = mb_entry(src + k, tb, p.tl.high_class);
+                    const uint32_t fw = e < 256u ? (e < 128u ? tb.ascii_feat[e] : 0u) : tb.class_feat[e - 256u];
+#pragma unroll
+                    for (int f = 0; f < NBASE; ++f) Pc[f] |= ((fw >> f) & 1u) << k;
+                }
+                Fc = sb;
+                squeeze_planes<NBASE>(Pc, Fc, leadc, valid);
+                nc = __popc(leadc);
+                int sc = nc;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += t; }
+                c0c = crun + sc - nc;
+                crun += __shfl_sync(FULL, sc, 31);
+                if (j == jt) c_hi = __shfl_sync(FULL, c0c + __popc(leadc & mask_lt(bt)), lt);
+            }
+            // -------------------------------------------------------------- context + rules of step j-1
+            if (j > 0) {
+                const int js = j - 1;
+                const int n = np, c0 = c0p;
+                const uint32_t Fm = Fp, lead = leadp;
+                uint32_t *P = Pp;
+                const uint32_t myLB = n > 0 ? ((((P[PL_A] >> (n - 1)) & 1u)) | (((P[PL_N] >> (n - 1)) & 1u) << 1) |
+                                               (((P[PL_LO] >> (n - 1)) & 1u) << 2) | (((P[PL_SP] >> (n - 1)) & 1u) << 3) |
+                                               (((P[PL_SY] >> (n - 1)) & 1u) << 4))
+                                            : 0u;
+                uint32_t LB = __shfl_up_sync(FULL, myLB, 1);
+                if (lane == 0) LB = prevLB;
+                prevLB = __shfl_sync(FULL, myLB, 31);
+                const int nl = (lane + 1) & 31;
+                const uint32_t XA = __shfl_sync(FULL, lane == 0 ? Pc[PL_A] : P[PL_A], nl), XN = __shfl_sync(FULL, lane == 0 ? Pc[PL_N] : P[PL_N], nl);
+                const uint32_t XLO = __shfl_sync(FULL, lane == 0 ? Pc[PL_LO] : P[PL_LO], nl), XSP = __shfl_sync(FULL, lane == 0 ? Pc[PL_SP] : P[PL_SP], nl);
+                const uint32_t XAT = __shfl_sync(FULL, lane == 0 ? Pc[PL_AT] : P[PL_AT], nl), XSL = __shfl_sync(FULL, lane == 0 ? Pc[PL_SL] : P[PL_SL], nl);
+                const uint32_t XF = __shfl_sync(FULL, lane == 0 ? Fc : Fm, nl);
+                const long long g0 = w0 + js * STEP + lane * 32;
+                const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
+                const uint32_t REAL = mask_lt(n - (has_term ? 1 : 0));
+                uint32_t TRUST = REAL;
+                if (js == RS - 1 && lane == 31 && !term_in_win) TRUST &= mask_lt(__popc(lead & mask_lt(32 - MARGIN)));
+                auto next1 = [&](uint32_t Xc, uint32_t Xn) -> uint32_t {
+                    const uint32_t l = Xc | __funnelshift_lc(0u, Xn, n), h = __funnelshift_lc(Xn, 0u, n);
+                    return __funnelshift_r(l, h, 1);
+                };
+                auto next2 = [&](uint32_t Xc, uint32_t Xn) -> uint32_t {
+                    const uint32_t l = Xc | __funnelshift_lc(0u, Xn, n), h = __funnelshift_lc(Xn, 0u, n);
+                    return __funnelshift_r(l, h, 2);
+                };
+                const uint32_t Lm_raw = next1(Fm, XF), L2m = next2(Fm, XF);
+                const uint32_t nF = ~Lm_raw, aF = ~(Lm_raw | L2m), pF = ~Fm;
+                const uint32_t Sraw = P[PL_SP];
+                uint32_t full[NFEAT];
+#pragma unroll
+                for (int f = 0; f < NBASE; ++f) full[f] = P[f];
+                full[12] = ((P[PL_A] << 1) | (LB & 1u)) & pF;                 // PREV_ALPHA
+                full[13] = next1(P[PL_A], XA) & nF;                           // NEXT_ALPHA
+                full[14] = ((P[PL_N] << 1) | ((LB >> 1) & 1u)) & pF;          // PREV_ALPHA_NUM
+                full[15] = next1(P[PL_N], XN) & nF;                           // NEXT_ALPHA_NUM
+                full[16] = ((P[PL_LO] << 1) | ((LB >> 2) & 1u)) & pF;         // PREV_LOWER
+                full[17] = next1(P[PL_LO], XLO) & nF;                         // NEXT_LOWER
+                full[18] = ((P[PL_SP] << 1) | ((LB >> 3) & 1u)) | Fm;         // PREV_SPACE  (start of string = space)
+                full[19] = next1(P[PL_SP], XSP) | Lm_raw;                     // NEXT_SPACE  (end of string = space)
+                full[20] = ((P[PL_SY] << 1) | ((LB >> 4) & 1u)) & pF;         // PREV_SYMBOL
+                full[21] = next1(P[PL_AT], XAT) & nF;                         // NEXT_AT
+                full[22] = next1(P[PL_SL], XSL) & nF;                         // NEXT_SLASH
+                full[23] = next2(P[PL_A], XA) & aF;                           // AFTER_NEXT_ALPHA
+                full[24] = next2(P[PL_SL], XSL) & aF;                         // AFTER_NEXT_SLASH
+                uint32_t CNT[NC], SYC[NY], Mraw;
+                if (kDefault) {
+                    // C_SPLIT: SPACE + SYMBOL + PREV_SYMBOL + UPPER*NEXT_LOWER + UPPER*PREV_LOWER (default_tokenizer.py:49-55);
+                    // up to 4 (UPPER is a Unicode property that some SYMBOL characters carry too), 5 with C_SYM: three planes
+                    const uint32_t t1 = full[5], t2 = full[6], t3 = full[20], t4 = full[4] & full[17], t5 = full[4] & full[16];
+                    const uint32_t s1 = t1 ^ t2 ^ t3, c1 = (t1 & t2) | (t3 & (t1 ^ t2));
+                    const uint32_t s2 = t4 ^ t5, c2 = t4 & t5;
+                    CNT[0] = s1 ^ s2;
+                    const uint32_t c3 = s1 & s2;
+                    CNT[1] = c1 ^ c2 ^ c3;
+                    CNT[2] = (c1 & c2) | (c3 & (c1 ^ c2));
+                    // C_MASK (default_tokenizer.py:80-91)
+                    Mraw = (full[7] & full[18] & full[13]) | (full[11] & full[18] & full[21] & full[23]) |
+                           (full[8] & full[14] & full[15]) | (full[9] & full[22] & full[24] & full[12]);
+                    // C_SYM: SYMBOL*NEXT_SPACE (default_tokenizer.py:100-102)
+                    SYC[0] = full[6] & full[19];
+                } else {
+                    auto term = [&](uint32_t mask) -> uint32_t {
+                        uint32_t a = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int f = 0; f < NFEAT; ++f) a &= full[f] | (((mask >> f) & 1u) - 1u);
+                        return a;
+                    };
+                    auto add1 = [&](uint32_t *c, int nb, uint32_t t) {
+                        for (int q = 0; q < nb; ++q) { const uint32_t k = c[q] & t; c[q] ^= t; t = k; }
+                    };
+#pragma unroll
+                    for (int q = 0; q < NC; ++q) CNT[q] = 0;
+#pragma unroll
+                    for (int q = 0; q < NY; ++q) SYC[q] = 0;
+                    Mraw = 0;
+                    for (int i = 0; i < p.rules.n_split; ++i) add1(CNT, NC, term(p.rules.split[i]));
+                    for (int i = 0; i < p.rules.n_mask; ++i) Mraw |= term(p.rules.mask[i]);
+                    for (int i = 0; i < p.rules.n_sym; ++i) add1(SYC, NY, term(p.rules.sym[i]));
+                }
+                // ---- chunk-aligned ownership (both neighbours look at the same bytes)
+                const uint32_t CLr = (Sraw | Lm_raw) & REAL;
+                if (js == 0 && r > 0) {
+                    uint32_t cand = lane < HLANES ? CLr : 0u;
+                    if (lane == HLANES - 1) cand &= mask_lt(__popc(lead & mask_lt(32 - MARGIN)));
+                    const unsigned bl = __ballot_sync(FULL, cand != 0u);
+                    lo_found = bl != 0u;
+                    const int fl = bl ? __ffs(bl) - 1 : 0;
+                    const int cv = __shfl_sync(FULL, c0 + __ffs(cand), fl);
+                    c_lo = lo_found ? cv : 0;
+                }
+                if (js == RS - 1 && !last_range) {
+                    uint32_t cand = lane >= 32 - HLANES ? CLr : 0u;
+                    if (lane == 31) cand &= mask_lt(__popc(lead & mask_lt(32 - MARGIN)));
+                    const unsigned bh = __ballot_sync(FULL, cand != 0u);
+                    closed = bh != 0u;
+                    const int fl = bh ? __ffs(bh) - 1 : 32 - HLANES;
+                    const int cv = __shfl_sync(FULL, closed ? c0 + __ffs(cand) : c0, fl);
+                    c_hi = cv;
+                }
+                // ---- forward half of the block mask, common case: a carry-propagating add per lane-word
+                uint32_t HOTorM = Mraw;
+                if (!exact) {
+                    const uint32_t ACTf = range_mask(c0, c_lo, CINF) & TRUST;
+                    const uint32_t Mm = Mraw & ACTf, CL = CLr & ACTf;
+                    uint32_t co;
+                    const uint32_t T0 = chunk_carry(Mm, CL, 0u, co);
+                    (void)T0;
+                    const unsigned G = __ballot_sync(FULL, co != 0u), Pg = __ballot_sync(FULL, CL == 0u && co == 0u);
+                    const unsigned long long sum = (unsigned long long)(G | Pg) + (unsigned long long)G + (unsigned long long)pend;
+                    const uint32_t cin = (((uint32_t)sum ^ Pg) >> lane) & 1u;
+                    pend = (uint32_t)(sum >> 32) & 1u;
+                    const uint32_t T = chunk_carry(Mm, CL, cin, co);
+                    HOTorM = T & CL;
+                    uint32_t dup = Mm & ~CL & T;
+                    if (js == RS - 1) dup &= range_mask(c0, c_lo, c_hi);
+                    dup_any |= dup;
+                }
+                // ---- park the step for pass C
+                {
+                    uint32_t *t = tempS + (js * 32 + lane) * TWD;
+                    const uint32_t pk = pack_ncp(n, c0, (int)((LB >> 3) & 1u));
+                    if (kDefault) {
+                        *reinterpret_cast<uint4 *>(t) = make_uint4(CNT[0], CNT[1], CNT[2], SYC[0]);
+                        *reinterpret_cast<uint4 *>(t + 4) = make_uint4(Sraw, Lm_raw, HOTorM, Fm);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NC; ++q) t[q] = CNT[q];
+#pragma unroll
+                        for (int q = 0; q < NY; ++q) t[4 + q] = SYC[q];
+                        t[8] = Sraw; t[9] = Lm_raw; t[10] = HOTorM; t[11] = Fm;
+                    }
+                    stateS[(js * SW + 5) * 32 + lane] = lead;
+                    stateS[(js * SW + 6) * 32 + lane] = pk;
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < NBASE; ++f) Pp[f] = Pc[f];
+            Fp = Fc; leadp = leadc; np = nc; c0p = c0c;
+        }
+        PROF5(1);
+        if (c_hi == CINF) c_hi = crun;           // (defensive; every range sets it)
+        n_own = c_hi - c_lo;
+        if (n_own < 0) n_own = 0;
+        if (!exact) {
+            irregular = !lo_found || !closed || __any_sync(FULL, dup_any != 0u);
+            if (irregular) return;               // the tile is analysed again by the exact evaluation
+        }
+        // temp accessors
+        auto T_S = [&](int js) -> uint32_t { return tempS[(js * 32 + lane) * TWD + (kDefault ? 4 : 8)]; };
+        auto T_L = [&](int js) -> uint32_t { return tempS[(js * 32 + lane) * TWD + (kDefault ? 5 : 9)]; };
+        auto T_H = [&](int js) -> uint32_t & { return tempS[(js * 32 + lane) * TWD + (kDefault ? 6 : 10)]; };
+        auto T_F = [&](int js) -> uint32_t { return tempS[(js * 32 + lane) * TWD + (kDefault ? 7 : 11)]; };
+        auto T_K = [&](int js) -> uint32_t { return stateS[(js * SW + 6) * 32 + lane]; };
+        auto real_mask = [&](int js, int n) -> uint32_t {
+            const long long g0 = w0 + js * STEP + lane * 32;
+            const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
+            return mask_lt(n - (has_term ? 1 : 0));
+        };
+        auto act_mask = [&](int js, int n, int c0) -> uint32_t {
+            const uint32_t REAL = real_mask(js, n);
+            if (closed) return range_mask(c0, c_lo, c_hi) & REAL;
+            uint32_t TRUST = REAL;
+            if (js == RS - 1 && lane == 31 && !term_in_win) TRUST &= mask_lt(__popc(stateS[(js * SW + 5) * 32 + lane] & mask_lt(32 - MARGIN)));
+            return range_mask(c0, c_lo, CINF) & TRUST;
+        };
+        // ---------------------------------------------------------------- pass B (exact only): backlog mark by mark
+        if (exact) {
+            int x = 0;
+            if (lane == 0) {
+                unsigned spins = 0;
+                while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xgen[warp])) != round) { if (++spins > (1u << 26)) break; }
+                x = ld_vs32(&ctl.xch[warp]);
+            }
+            x = __shfl_sync(FULL, x, 0);
+            int v_nom = 0;
+#pragma unroll 1
+            for (int js = 0; js < RS; ++js) {
+                const uint32_t pk = T_K(js);
+                const int n = pk_n(pk), c0 = pk_c0(pk);
+                const uint32_t ACT = act_mask(js, n, c0);
+                const uint32_t S = T_S(js) & ACT, Lm = T_L(js) & ACT, Mm = T_H(js) & ACT, FmA = T_F(js) & ACT;
+                uint32_t HOT = 0;
+                int xin = 0, out = 0;
+                if (Mm) out = eval_backlog(0, Mm, FmA, S, Lm, HOT);
+                for (;;) {
+                    int nx = __shfl_up_sync(FULL, out, 1);
+                    if (lane == 0) nx = x;
+                    const bool ch = nx != xin;
+                    if (!__any_sync(FULL, ch)) break;
+                    if (ch) { xin = nx; if (xin != 0 || Mm) out = eval_backlog(xin, Mm, FmA, S, Lm, HOT); else { out = 0; HOT = 0; } }
+                }
+                x = __shfl_sync(FULL, out, 31);
+                if (js == RS - 1) v_nom = __shfl_sync(FULL, out, 32 - HLANES - 1);
+                T_H(js) = HOT;
+            }
+            v_out = closed ? x : v_nom;
+            if (lane == 0) {
+                st_vs32(&ctl.xch[warp + 1], v_out);
+                __threadfence_block();
+                st_vs32(reinterpret_cast<int *>(&ctl.xgen[warp + 1]), (int)round);
+            }
+            // the chunk still open at the end of the trusted halo: hot if a backlog is pending, else look ahead for a mark
+            if (!closed) {
+                const uint32_t pk = T_K(RS - 1);
+                const int n = pk_n(pk), c0 = pk_c0(pk);
+                const uint32_t ACT = act_mask(RS - 1, n, c0);
+                const uint32_t CL = (T_S(RS - 1) | T_L(RS - 1)) & ACT;
+                const unsigned H = __ballot_sync(FULL, CL != 0u);
+                const unsigned above = H & (0xFFFFFFFFu << (32 - HLANES));
+                bool nw = false;
+                if (lane == 32 - HLANES - 1) {
+                    const int nr = __popc(ACT);
+                    nw = nr > 0 && ((CL >> (nr - 1)) & 1u) == 0u && above == 0u;
+                }
+                const bool need_walk = __shfl_sync(FULL, nw ? 1 : 0, 32 - HLANES - 1) != 0;
+                if (need_walk) {
+                    if (x >= 1) far = 1;
+                    else {
+                        const bool any = walk_ahead(p, tb, w0 + WIN - MARGIN, lane);
+                        far = any ? 1 : 0;
+                        if (lane == 0) atomicAdd(&p.result->walks, 1ull);
+                    }
+                }
+            }
+        }
+        PROF5(2);
+        // ---------------------------------------------------------------- pass C: blanked chunks, values, tokens
+        {
+            uint32_t bin_step = (uint32_t)far;
+            int nsa_carry = -1;
+            int lft_max = -1;
+#pragma unroll 1
+            for (int js = RS - 1; js >= 0; --js) {
+                const uint32_t *t = tempS + (js * 32 + lane) * TWD;
+                uint32_t CNT[NC], SYC[NY], Sraw, Lr, HOT, Fm, pk;
+                if (kDefault) {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(t), b4 = *reinterpret_cast<const uint4 *>(t + 4);
+                    CNT[0] = a.x; CNT[1] = a.y; CNT[2] = a.z; SYC[0] = a.w; Sraw = b4.x; Lr = b4.y; HOT = b4.z; Fm = b4.w;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NC; ++q) CNT[q] = t[q];
+#pragma unroll
+                    for (int q = 0; q < NY; ++q) SYC[q] = t[4 + q];
+                    Sraw = t[8]; Lr = t[9]; HOT = t[10]; Fm = t[11];
+                }
+                pk = stateS[(js * SW + 6) * 32 + lane];
+                const int n = pk_n(pk), c0 = pk_c0(pk);
+                const uint32_t REAL = real_mask(js, n);
+                const uint32_t OWN = range_mask(c0, c_lo, c_hi) & REAL;
+                const uint32_t ACT = closed ? OWN : act_mask(js, n, c0);
+                const uint32_t CL = (Sraw | Lr) & ACT;
+                HOT &= CL;
+                const bool hasCL = CL != 0u;
+                const bool firstHot = hasCL && (HOT & (CL & (0u - CL))) != 0u;
+                const unsigned H = __ballot_sync(FULL, hasCL), FH = __ballot_sync(FULL, firstHot);
+                const unsigned above = lane == 31 ? 0u : (H & (0xFFFFFFFFu << (lane + 1)));
+                const uint32_t bin = above ? ((FH >> (__ffs(above) - 1)) & 1u) : bin_step;
+                if (H) bin_step = (FH >> (__ffs(H) - 1)) & 1u;
+                const uint32_t Zm = flood_down(HOT, CL, bin);
+                const uint32_t keepm = ~Zm | Sraw;             // block mask = 1
+                // split values: splits = split_cnt * block_mask + sym; splits[0] = 1 (default_tokenizer.py:121-132)
+                uint32_t V[NV];
+                if (kDefault) {
+                    const uint32_t x0 = CNT[0] & keepm, x1 = CNT[1] & keepm, x2 = CNT[2] & keepm, y = SYC[0];
+                    V[0] = x0 ^ y;
+                    const uint32_t k0 = x0 & y;
+                    V[1] = x1 ^ k0;
+                    V[2] = x2 ^ (x1 & k0);
+                } else {
+                    uint32_t carry = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t xq = CNT[q] & keepm, y = SYC[q];
+                        V[q] = xq ^ y ^ carry;
+                        carry = (xq & y) | (carry & (xq ^ y));
+                    }
+                    V[4] = carry;
+                }
+                V[0] |= Fm;
+#pragma unroll
+                for (int q = 1; q < NV; ++q) V[q] &= ~Fm;
+                uint32_t SPLIT = 0;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) SPLIT |= V[q];
+                const uint32_t PS = (Sraw << 1) | pk_ps(pk);
+                const uint32_t E = ((SPLIT & ~Sraw) | (~SPLIT & PS & ~Fm)) & OWN;     // a token is counted at this character
+                int ts = __popc(E);
+                const int mytok = ts;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int q = __shfl_up_sync(FULL, ts, d); if (lane >= d) ts += q; }
+                const int tot = __shfl_sync(FULL, ts, 31);
+                ntok_range += tot;
+                // first split that can end a token, for the steps before this one
+                const uint32_t SPq = SPLIT & mask_lt(n) & range_mask(c0, c_lo, closed ? c_hi + 1 : c_hi);
+                const unsigned hs = __ballot_sync(FULL, SPq != 0u);
+                const int firstsp = __shfl_sync(FULL, c0 + __ffs(SPq) - 1, hs ? __ffs(hs) - 1 : 0);
+                if (lane == 0) { ctl.tokstep[warp][js] = tot; ctl.nsa[warp][js] = nsa_carry; }
+                if (hs) nsa_carry = firstsp;
+                const uint32_t FO = Fm & OWN;
+                if (FO) lft_max = max(lft_max, c0 + 31 - __clz(FO));
+                // state for pass D
+                uint32_t *st = stateS + js * SW * 32 + lane;
+                st[0] = V[0]; st[32] = V[1]; st[64] = V[2]; st[96] = E; st[128] = Fm;
+                st[192] = (pk & 0xC007FFFFu) | ((uint32_t)(ts - mytok) << 19);
+                if (!kDefault) { uint32_t *t2 = tempS + (js * 32 + lane) * TWD; t2[13] = V[3]; t2[14] = V[4]; }
+            }
+            lft = __reduce_max_sync(FULL, lft_max);
+            __syncwarp();
+        }
+        PROF5(3);
+    };
+
+    // ================================================================================================= output
+    auto output = [&](unsigned long long G_in, unsigned long long K_in, unsigned long long base_in, bool direct_spans) {
+        if (!have) return;
+        if (K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens && lane == 0) atomicOr(&p.result->error, 4u);
+        if (G_in + (unsigned long long)n_own > (unsigned long long)p.n_bytes || K_in + (unsigned long long)ntok_range > (unsigned long long)p.n_bytes + 1ull) {
+            if (lane == 0 && atomicOr(&p.result->error, 8u) == 0u) {
+                p.result->prof[8] = (unsigned long long)r; p.result->prof[9] = G_in; p.result->prof[10] = K_in;
+                p.result->prof[11] = (unsigned long long)(long long)n_own; p.result->prof[12] = (unsigned long long)(long long)ntok_range;
+                p.result->prof[13] = (unsigned long long)(long long)c_lo; p.result->prof[14] = (unsigned long long)(long long)c_hi;
+            }
+            return;
+        }
+        // range-relative character index of the first character of the string that is open at c_lo (may be negative)
+        int cur_base = c_lo - (int)(long long)(G_in - base_in);
+        int ktok = 0;                      // tokens of the range before this step
+        long long qn = p.tile_first_str[r];
+        uint32_t prev_tailw = 0;
+        const bool spans_direct_all = direct_spans || !closed || !lo_found;
+#pragma unroll 1
+        for (int js = 0; js < RS; ++js) {
+            const uint32_t *st = stateS + js * SW * 32 + lane;
+            uint32_t V[NV];
+            V[0] = st[0]; V[1] = st[32]; V[2] = st[64];
+            if (!kDefault) { const uint32_t *t2 = tempS + (js * 32 + lane) * TWD; V[3] = t2[13]; V[4] = t2[14]; }
+            const uint32_t E = st[96], Fm = st[128], lead = st[160], pk = st[192];
+            const int n = pk_n(pk), c0 = pk_c0(pk), tp = pk_tp(pk);
+            const long long g0 = w0 + js * STEP + lane * 32;
+            const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
+            const uint32_t REAL = mask_lt(n - (has_term ? 1 : 0));
+            const uint32_t OWN = range_mask(c0, c_lo, c_hi) & REAL;
+            const int cstep0 = __shfl_sync(FULL, c0, 0), cstep1 = __shfl_sync(FULL, c0 + n, 31);
+            const int cf = max(c_lo, cstep0), cend = min(c_hi, cstep1);     // owned characters of this step: [cf, cend)
+            const int nb = cend - cf;
+            const int ntok_step = ctl.tokstep[warp][js];
+            uint32_t SPLIT = 0;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) SPLIT |= V[q];
+            // ------------------------------------------------------------ split mask bytes
+            if (want_splits && nb > 0) {
+                const unsigned long long Gf = G_in + (unsigned long long)(cf - c_lo);
+                const int a = (int)(Gf & 15ull);
+                uint32_t W[8];
+                if (kDefault) {
+                    const uint32_t qlo = (V[0] & 0x0F0F0F0Fu) | ((V[1] & 0x0F0F0F0Fu) << 4);
+                    const uint32_t qhi = ((V[0] >> 4) & 0x0F0F0F0Fu) | (V[1] & 0xF0F0F0F0u);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        W[2 * g] = lutv[(qlo >> (8 * g)) & 0xFFu];
+                        W[2 * g + 1] = lutv[(qhi >> (8 * g)) & 0xFFu];
+                    }
+                    if (V[2]) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) W[g] += spread4((V[2] >> (4 * g)) & 15u) << 2;
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        uint32_t w = 0;
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) w += spread4((V[q] >> (4 * g)) & 15u) << q;
+                        W[g] = w;
+                    }
+                }
+                uint32_t tailw = 0;       // the last 4 characters of this lane, for the next lane's first word
+                if (n >= 4) {
+                    const int sft = n - 4;
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) tailw += spread4((V[q] >> sft) & 15u) << q;
+                }
+                uint32_t headw = __shfl_up_sync(FULL, tailw, 1);
+                if (lane == 0) headw = prev_tailw;
+                const long long gfull = p.n_bytes - g0;
+                const bool slow = __any_sync(FULL, gfull >= 32 && n < 4);       // malformed UTF-8 only
+                const int o = SPAD + a + (c0 - cf);                 // staging offset of this lane's first character
+                if (o >= 4 && n > 0) {
+                    if (!slow) {
+                        // words are written by the lane that owns their LAST byte: no partial words, no races
+                        const int s = o & 3;
+                        const int cnt = (s + n) >> 2;
+                        uint32_t *dst = reinterpret_cast<uint32_t *>(sst) + (o >> 2);
+                        const int sh = 32 - 8 * s;
+                        uint32_t prev = headw;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t w = s ? __funnelshift_r(prev, W[i], sh) : W[i];
+                            if (i < cnt) dst[i] = w;
+                            prev = W[i];
+                        }
+                        if (8 < cnt) dst[8] = __funnelshift_r(prev, 0u, sh);
+                        // the lane that holds the last owned character of the step flushes the trailing partial word
+                        if (c0 < cend && c0 + n >= cend) {
+                            const int end = SPAD + a + nb;
+                            for (int q = end & ~3; q < end; ++q) {
+                                const int jj = q - o;
+                                const uint32_t srcw = jj >= 0 ? W[jj >> 2] >> ((jj & 3) * 8) : headw >> ((4 + jj) * 8);
+                                sst[q] = (uint8_t)(srcw & 0xFFu);
+                            }
+                        }
+                    } else {
+                        for (int jj = 0; jj < n; ++jj) {
+                            uint32_t vv = 0;
+#pragma unroll
+                            for (int q = 0; q < NV; ++q) vv |= ((V[q] >> jj) & 1u) << q;
+                            sst[o + jj] = (uint8_t)vv;
+                        }
+                    }
+                }
+                prev_tailw = __shfl_sync(FULL, tailw, 31);
+                __syncwarp();
+                int8_t *dst = p.splits + Gf;
+                const uint8_t *srcb = sst + SPAD + a;
+                const int hb = min((16 - a) & 15, nb);
+                if (lane < hb) dst[lane] = (int8_t)srcb[lane];
+                const int nch = (nb - hb) >> 4;
+                for (int i = lane; i < nch; i += 32)
+                    *reinterpret_cast<uint4 *>(dst + hb + 16 * i) = *reinterpret_cast<const uint4 *>(srcb + hb + 16 * i);
+                const int done = hb + (nch << 4);
+                if (lane < nb - done) dst[done + lane] = (int8_t)srcb[done + lane];
+                __syncwarp();
+            } else if (want_splits) {
+                prev_tailw = 0;
+            }
+            // ------------------------------------------------------------ token spans
+            // latest owned string start in the lanes before this one (else: the one open when the step began)
+            const uint32_t FO = Fm & OWN;
+            int lf_excl;
+            {
+                const int mine = FO ? c0 + 31 - __clz(FO) : -1;
+                const unsigned has = __ballot_sync(FULL, FO != 0u);
+                const unsigned below = has & mask_lt(lane);
+                const int got = __shfl_sync(FULL, mine, below ? 31 - __clz(below) : 0);
+                lf_excl = below ? got : cur_base;
+                const int wlast = __shfl_sync(FULL, mine, has ? 31 - __clz(has) : 0);
+                if (has) cur_base = wlast;      // (for the next step; this step uses lf_excl)
+            }
+            if (want_spans) {
+                const unsigned long long Ks = K_in + (unsigned long long)ktok;
+                const bool direct = spans_direct_all || ntok_step > TCAP;
+                const int ka = (int)(Ks & 1ull);
+                // one (start, end) pair per token; end = next split (a string start is always a split)
+                const uint32_t SPq = SPLIT & mask_lt(n) & range_mask(c0, c_lo, closed ? c_hi + 1 : c_hi);
+                const int myfirst = SPq ? c0 + __ffs(SPq) - 1 : -1;
+                const unsigned hs = __ballot_sync(FULL, myfirst >= 0);
+                int nextsplit;     // first split in the following lanes / steps (-1: none in this range)
+                {
+                    const unsigned above = lane == 31 ? 0u : (hs & (0xFFFFFFFFu << (lane + 1)));
+                    const int got = __shfl_sync(FULL, myfirst, above ? __ffs(above) - 1 : 0);
+                    nextsplit = above ? got : ctl.nsa[warp][js];
+                }
+                uint32_t ev = E;
+                int rank = 0;
+                int cbase = lf_excl;
+                while (ev) {
+                    const int i = __ffs(ev) - 1; ev &= ev - 1;
+                    const uint32_t fb = FO & mask_lt(i + 1);
+                    if (fb) cbase = c0 + 31 - __clz(fb);
+                    const uint32_t ab = (i == 31) ? 0u : (SPq & (0xFFFFFFFEu << i));
+                    const int endc = ab ? c0 + __ffs(ab) - 1 : nextsplit;
+                    const int sidx = c0 + i - (((SPLIT >> i) & 1u) ? 0 : 1) - cbase;
+                    const int eidx = endc >= 0 ? endc - cbase : -1;
+                    if (!direct) tst[ka + tp + rank] = make_int2(sidx, eidx);
+                    else {
+                        const long long kk = (long long)Ks + tp + rank;
+                        if (kk < p.cap_tokens) {
+                            if (eidx >= 0) reinterpret_cast<int2 *>(p.spans)[kk] = make_int2(sidx, eidx);
+                            else p.spans[2 * kk] = sidx;          // still open: a later range writes the end
+                        }
+                    }
+                    ++rank;
+                }
+                // a range whose head is not chunk-aligned: its first split that follows a non-space character ends the
+                // token left open by earlier ranges (exact evaluation only; the temp words are still in place)
+                if (!lo_found && r > 0) {
+                    const uint32_t Sraw = tempS[(js * 32 + lane) * TWD + (kDefault ? 4 : 8)];
+                    const uint32_t PSr = (Sraw << 1) | pk_ps(pk);
+                    const uint32_t END = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo, last_range ? c_hi + 1 : c_hi);
+                    if (END) {
+                        const int i = __ffs(END) - 1;
+                        if (ktok + tp + __popc(E & mask_lt(i)) == 0) {
+                            const uint32_t fb = FO & mask_lt(i);      // string starts strictly before the split
+                            const int cb = fb ? c0 + 31 - __clz(fb) : lf_excl;
+                            const long long kk = (long long)K_in - 1;
+                            if (kk >= 0 && kk < p.cap_tokens) p.spans[2 * kk + 1] = c0 + i - cb;
+                        }
+                    }
+                }
+                if (!direct) {
+                    __syncwarp();
+                    int2 *dst = reinterpret_cast<int2 *>(p.spans) + Ks;
+                    long long room = p.cap_tokens - (long long)Ks;
+                    const int nt = room <= 0 ? 0 : (room < ntok_step ? (int)room : ntok_step);
+                    const int hb = min(ka, nt);                       // pairs in front of the first 16-byte boundary
+                    if (lane < hb) dst[lane] = tst[ka + lane];
+                    const int nch = (nt - hb) >> 1;
+                    for (int i = lane; i < nch; i += 32)
+                        *reinterpret_cast<uint4 *>(dst + hb + 2 * i) = *reinterpret_cast<const uint4 *>(tst + ka + hb + 2 * i);
+                    const int done = hb + 2 * nch;
+                    if (lane < nt - done) dst[done + lane] = tst[ka + done + lane];
+                    __syncwarp();
+                }
+            }
+            // ------------------------------------------------------------ CSR offsets of the strings that start in this step
+            {
+                const long long sbeg = w0 + (long long)js * STEP, send = sbeg + STEP;
+                for (;;) {
+                    const long long q = qn + lane;
+                    const long long o = q <= p.n_strings ? p.offsets[q] : 0x7FFFFFFFFFFFFFFFLL;
+                    const bool in = o < send;
+                    const int wb = in ? int(o - sbeg) : 0;
+                    const int tl = (wb >> 5) & 31;
+                    const uint32_t l_lead = __shfl_sync(FULL, lead, tl), l_E = __shfl_sync(FULL, E, tl);
+                    const int l_c0 = __shfl_sync(FULL, c0, tl), l_tp = __shfl_sync(FULL, tp, tl);
+                    if (in) {
+                        const int c = l_c0 + __popc(l_lead & mask_lt(wb & 31));
+                        const bool mine = last_range ? (c >= c_lo) : (c >= c_lo && c < c_hi);
+                        if (mine) {
+                            p.char_off[q] = (long long)(G_in + (unsigned long long)(c - c_lo));
+                            p.tok_off[q] = (long long)K_in + ktok + l_tp + __popc(l_E & mask_lt(c - l_c0));
+                        }
+                    }
+                    const int cnt = __popc(__ballot_sync(FULL, in));
+                    qn += cnt;
+                    if (cnt < 32) break;
+                }
+            }
+            ktok += ntok_step;
+        }
+        if (last_range && lane == 0) {
+            p.result->n_chars = G_in + (unsigned long long)n_own;
+            p.result->n_tokens = K_in + (unsigned long long)ntok_range;
+        }
+    };
+
+    // ================================================================================================= main loop
+    unsigned xphase = 0, round = 0;
+    long long tile = ctl.tile_id[0];
+    bool tma_pending = false;
+    if (tile < p.ntiles) tma_pending = begin_load(tile * NW + warp);
+    for (int k = 0; tile < p.ntiles; ++k) {
+        const int s = k & 1;
+        r = tile * NW + warp; w0 = r * (long long)RANGE;
+        have = r < p.nranges; last_range = r == p.nranges - 1;
+        if (tma_pending) {
+            unsigned spins = 0;
+            while (!mbar_try_wait(mbar + warp, xphase)) {
+                if (++spins > (1u << 24)) { if (lane == 0) atomicOr(&p.result->error, 1u); break; }   // watchdog: never hang the device
+            }
+            xphase ^= 1u;
+        }
+        __syncwarp();
+        PROF5(0);
+        analyze(false, 0u);
+        bool exact_done = false;
+        for (;;) {
+            if (lane == 0) {
+                WAgg &a = ctl.wagg[s][warp];
+                a.n_own = n_own; a.ntok = ntok_range; a.lft = lft >= 0 ? lft - c_lo : -1; a.v = v_out; a.flags = irregular ? 1 : 0;
+                __threadfence_block();
+            }
+            __syncwarp();
+            nb_arrive(BAR_AGG + s, NTH);
+            nb_sync(BAR_PRE + s, NTH);
+            if (ctl.slot[s].mode == 0) break;
+            ++round;
+            if (have) plain_load(r);
+            analyze(true, round);
+            exact_done = true;
+        }
+        PROF5(4);
+        // own prefix: the tile's plus the ranges before this one
+        unsigned long long G_in, K_in, base_in;
+        {
+            const Slot sl = ctl.slot[s];
+            const WAgg a = ctl.wagg[s][lane < NW ? lane : 0];
+            const bool before = lane < warp;
+            const int pn = __reduce_add_sync(FULL, before ? a.n_own : 0), pk = __reduce_add_sync(FULL, before ? a.ntok : 0);
+            int pnx = lane < NW ? a.n_own : 0;            // exclusive prefix of characters per range
+            {
+                int inc = pnx;
+#pragma unroll
+                for (int d = 1; d < NW; d <<= 1) { const int t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
+                pnx = inc - pnx;
+            }
+            const unsigned hl = __ballot_sync(FULL, before && a.lft >= 0);
+            const int lv = __shfl_sync(FULL, pnx + a.lft, hl ? 31 - __clz(hl) : 0);
+            G_in = sl.G + (unsigned long long)pn; K_in = sl.K + (unsigned long long)pk;
+            base_in = hl ? sl.G + (unsigned long long)lv : sl.base;
+        }
+        const long long tnext = ctl.tile_id[s ^ 1];
+        tma_pending = false;
+        // the next window is fetched while this one is written out (the exact path still reads the temp words that live
+        // in the window buffer, so there it waits)
+        const bool early = kDefault && !exact_done;
+        if (tnext < p.ntiles && early) tma_pending = begin_load(tnext * NW + warp);
+        output(G_in, K_in, base_in, exact_done);
+        if (tnext < p.ntiles && !early) tma_pending = begin_load(tnext * NW + warp);
+        PROF5(5);
+        tile = tnext;
+    }
+}
+
+template <bool kDefault>
+static cudaError_t launch_one(const Params &p, int grid, cudaStream_t s)
+{
+    const size_t smem = (size_t)plan(p.tl, kDefault).total;
+    static size_t configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(tokenize5_kernel<kDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    tokenize5_kernel<kDefault><<<grid, NTH, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace v5
+
+int tokenize5_range_bytes() { return v5::RANGE; }
+int tokenize5_ranges_per_tile() { return v5::NW; }
+
+int tokenize5_ctas_per_sm(const TableLayout &tl, bool is_default)
+{
+    int nb = 0;
+    const size_t smem = (size_t)v5::plan(tl, is_default).total;
+    cudaError_t e;
+    if (is_default) { cudaFuncSetAttribute(v5::tokenize5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v5::tokenize5_kernel<true>, v5::NTH, smem); }
+    else { cudaFuncSetAttribute(v5::tokenize5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v5::tokenize5_kernel<false>, v5::NTH, smem); }
+    if (e != cudaSuccess) { cudaGetLastError(); return 1; }
+    return nb < 1 ? 1 : nb;
+}
+
+cudaError_t launch_tokenize5(const Params &p, int grid, cudaStream_t s)
+{
+    return p.rules.is_default ? v5::launch_one<true>(p, grid, s) : v5::launch_one<false>(p, grid, s);
+}
+
+}  // namespace latok

@@ -12,7 +12,10 @@ from oracle import oracle
 pytestmark = pytest.mark.gpu
 
 ALL = 1 | 2 | 4 | 8
-TILE = 16128  # owned bytes per tile (latok_internal.h); tests place interesting things around multiples of it
+# bytes owned per unit of work (latok_internal.h): a v5 range (one warp), a v4 tile (token-feature / matrix modes) and a
+# v5 tile (8 ranges, one look-back record); tests place interesting things around multiples of each
+UNITS = (3968, 7936, 31744)
+TILE = 7936
 
 
 @pytest.fixture(scope="module")
@@ -24,6 +27,9 @@ def engine():
 
 
 def check_batch(engine, texts, what=ALL, rules=None, label=""):
+    if (what & 12) and (what & 3):
+        # split mask + spans alone run the v5 kernel, anything with token features / the matrix the v4 kernel: check both
+        check_batch(engine, texts, what & 3, rules, label + " [splits+spans only]")
     r = engine.run(texts, what)
     o = oracle.tokenize_batch(texts, rules=rules or oracle.DEFAULT_RULES, matrix=bool(what & 8), feats=bool(what & 4))
     assert r.n_chars == o["n_chars"], label
@@ -114,9 +120,10 @@ def _long_doc(rng, n_chars, profile="ascii"):
 
 def test_long_documents_cross_tiles(engine):
     rng = np.random.default_rng(42)
-    docs = [_long_doc(rng, int(n), p) for n, p in [(70000, "ascii"), (50000, "mixed"), (33000, "marks"),
-                                                   (TILE, "ascii"), (TILE + 1, "ascii"), (TILE - 1, "ascii"),
-                                                   (2 * TILE, "ascii"), (100, "ascii"), (3 * TILE + 5, "mixed")]]
+    sizes = [(70000, "ascii"), (50000, "mixed"), (33000, "marks"), (100, "ascii")]
+    for u in UNITS:
+        sizes += [(u, "ascii"), (u + 1, "ascii"), (u - 1, "ascii"), (2 * u, "ascii"), (3 * u + 5, "mixed")]
+    docs = [_long_doc(rng, int(n), p) for n, p in sizes]
     check_batch(engine, docs, label="long docs")
 
 
@@ -124,22 +131,32 @@ def test_boundary_alignment_sweep(engine):
     """Slide interesting patterns across the tile boundary one byte at a time."""
     patterns = ["a@b.c", " #tag ", "x http://t.co/abc y", "fooBar", ".@joe ", "éè 日本 \U0001F600!", "a, b",
                 "  ", "!! ", "e@f,g@h,i@j one,two three,four "]
+    for unit in UNITS:
+        texts = []
+        for pat in patterns:
+            for shift in range(-8, 6):
+                pad = unit + shift - 3
+                texts.append("w" * 5 + " " + "z" * (pad - 6) + pat + " tail end")
+        check_batch(engine, texts, label=f"alignment sweep {unit} (one string per case)")
+        # same but as one long string so the boundary falls inside a string at many different phases
+        check_batch(engine, [" ".join(texts[:20])], label=f"alignment sweep {unit} (joined)")
+    # the same patterns against the 1 KB steps inside a range and against the 116-byte closer search windows
     texts = []
     for pat in patterns:
-        for shift in range(-8, 6):
-            pad = TILE + shift - 3
-            texts.append("w" * 5 + " " + "z" * (pad - 6) + pat + " tail end")
-    check_batch(engine, texts, label="alignment sweep (one string per case)")
-    # same but as one long string so the boundary falls inside a string at many different phases
-    check_batch(engine, [" ".join(texts[:20])], label="alignment sweep (joined)")
+        for base in (1024, 2048, 3072, 3968 + 116, 3968 + 128, 4096, 2 * 3968 + 116):
+            for shift in range(-6, 5):
+                texts.append("q r " + "z" * (base + shift - 8) + " " + pat + " tail end")
+    check_batch(engine, texts, label="alignment sweep (steps / search windows)")
 
 
 def test_multibyte_straddling_tiles(engine):
     for ch in ["é", "日", "\U0001F600", "　", " "]:
         n = len(ch.encode("utf-8"))
         texts = []
-        for shift in range(0, 6):
-            texts.append("a" * (TILE - shift) + ch * 40 + " b")
+        for unit in UNITS + (1024, 2048, 4096):
+            for shift in range(0, 6):
+                texts.append("a" * (unit - shift) + ch * 40 + " b")
+                texts.append("a b " * ((unit - shift) // 4 - 1) + "a" * ((unit - shift) % 4 + 4) + ch * 40 + " b")
         check_batch(engine, texts, label=f"straddle {ch!r} ({n} bytes)")
 
 
@@ -147,8 +164,9 @@ def test_long_space_free_runs_and_walk(engine):
     """Chunks longer than the right halo force the look-ahead walk; marks far ahead must blank
     characters in earlier tiles (latok.c:218-244 has unbounded reach)."""
     cases = []
-    for run in (300, 1000, TILE - 50, TILE + 300, 2 * TILE + 77, 40000):
-        base = "x" * (TILE - 120)
+    for TILE, run in ((7936, 300), (7936, 1000), (7936, 7936 - 50), (7936, 7936 + 300), (7936, 2 * 7936 + 77), (7936, 40000),
+                      (3968, 100), (3968, 130), (3968, 3968 + 300), (31744, 200), (31744, 31744 + 5000), (3968, 70000)):
+        base = "x y " * ((TILE - 120) // 4)
         cases.append(base + " " + ",".join(["ab"] * (run // 3)) + " end")                    # no mark: commas split
         cases.append(base + " " + ",".join(["ab"] * (run // 3)) + ",q@r end")                # mark at the very end
         cases.append(base + " " + ",".join(["ab"] * (run // 3)) + ",http://x.y/z end")
@@ -158,7 +176,7 @@ def test_long_space_free_runs_and_walk(engine):
     r = check_batch(engine, cases, label="space-free runs")
     assert r.lookahead_walks > 0
     # multibyte inside the long run
-    check_batch(engine, ["y" * (TILE - 100) + " " + "日、" * 3000 + "a@b 日 end"], label="cjk run")
+    check_batch(engine, ["y" * (u - 100) + " " + "日、" * 3000 + "a@b 日 end" for u in UNITS], label="cjk run")
 
 
 def test_backlog_across_tiles(engine):
@@ -166,9 +184,11 @@ def test_backlog_across_tiles(engine):
     cross tile boundaries and string boundaries (it must reset at each string start)."""
     many = ",".join(f"a{i}@b" for i in range(40))
     words = " ".join(f"w{i},x" for i in range(60))
-    texts = [
-        "p" * (TILE - 200) + " " + many + " " + words,
-        "p" * (TILE - 30) + " " + many + " " + words,
+    texts = []
+    for u in UNITS:
+        texts += ["p" * (u - 200) + " " + many + " " + words, "p" * (u - 30) + " " + many + " " + words,
+                  "p q " * ((u - 200) // 4) + many + " " + words, "p q " * ((u - 40) // 4) + many + " " + words]
+    texts += [
         many + " " + " ".join(f"w{i},x" for i in range(3000)),
         ",".join(f"a{i}@b" for i in range(5000)) + " " + " ".join(f"w{i},x" for i in range(6000)),
         many, words, many + " " + words,
