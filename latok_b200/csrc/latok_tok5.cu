@@ -20,6 +20,9 @@
 //   -> the service warp sums the 8 ranges, publishes the tile aggregate, looks back, hands the prefix down
 //   pass D  forward: split bytes and (start,end) pairs staged per step in shared memory and written with
 //           aligned 16-byte stores; CSR offsets by one lane per string.
+// The warps run one tile ahead of the look-back: analysis of tile k+1, then pass D of tile k, whose state waits in
+// place of its input bytes (two window buffers per warp).  Tickets are taken by the first warp that is ready for the
+// next tile, so ticket order follows start order and predecessors publish first.
 //
 // No tensor cores: nothing here is a dense contraction; the bound is HBM bandwidth.
 #include "latok_device.cuh"
@@ -40,41 +43,46 @@ constexpr int LPAD = 16;                 // bytes in front of the window (previo
 constexpr int XBYTES = LPAD + WIN + 16;
 constexpr int SPAD = 160;                // slack in front of the first owned character in the split stage
 constexpr int SSTAGE = SPAD + 16 + STEP + 48;
-constexpr int TCAP = 256;                // tokens staged per step; steps with more write their pairs directly
+constexpr int TCAP = 320;                // tokens staged per step; steps with more write their pairs directly
 constexpr int TSTAGE = (TCAP + 2) * 8;
-constexpr int SW = 7;                    // state words per lane and step handed from pass C to pass D: V0 V1 V2 E F lead packed
+constexpr int TWG = 12;                  // generic rules: words per lane-word in the (separate) state buffers
 enum { BAR_AGG = 1, BAR_PRE = 3 };
 static_assert(RANGE == WIN - HALO && HALO % 32 == 0 && RANGE % 16 == 0, "geometry");
 
 struct WAgg { int n_own, ntok, lft, v, flags, pad[3]; };
 struct Slot { unsigned long long G, K, base; int mode, x_in; };
+struct RInfo { int c_lo, c_hi, n_own, ntok, flags, pad[3]; };    // flags: 1 have, 2 closed, 4 lo_found, 8 last_range
 struct Ctl {
-    long long tile_id[2];
+    int tile_id[2], tk_cnt[2], tk_flag[2], pad0[2];
     Slot slot[2];
     WAgg wagg[2][NW];
     int xch[NW + 1];
     unsigned xgen[NW + 1];
-    int tokstep[NW][RS];                 // tokens per step
-    int nsa[NW][RS];                     // first split after the step (range-relative character index, -1: none)
+    RInfo rinfo[NW][2];
+    int tokstep[NW][2][RS];              // tokens per step
+    int nsa[NW][2][RS];                  // first split after the step (range-relative character index, -1: none)
 };
 
+// Per lane-word, between the passes, 8 words live IN PLACE of the lane-word's 32 input bytes (default rules):
+//   after pass A : CNT0 CNT1 CNT2 SYM | S  M/HOT  F  packed        after pass C : V0 V1 V2 E | S  -  F  packed
+// (generic rules: TWG words in a separate buffer: CNT[4] SYM[4] S M/HOT F packed -> V[5] E - - S - F packed);
+// the string-start map of the window (bit = byte) turns into the lane-word's lead-byte mask once it has been read.
 struct Plan {
-    int tables, ctl, mbar, warp0, x, sst, tst, sbm, state, temp, per_warp, total;
+    int tables, ctl, mbar, warp0, x[2], sst, tst, sbm[2], temp[2], per_warp, total;
 };
 __host__ __device__ inline Plan plan(const TableLayout &tl, bool is_default)
 {
     Plan s; int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
-    s.tables = take(tl.total - tl.lutv);
+    s.tables = take(tl.stage2 - tl.lutv);    // split-value LUT, ASCII / class feature words, stage 1; stage 2 (16 KB) stays in global memory (L1)
     s.ctl = take((int)sizeof(Ctl));
-    s.mbar = take(8 * NW);
+    s.mbar = take(8 * 2 * NW);
     s.warp0 = o;
-    s.x = take(XBYTES);
+    s.x[0] = take(XBYTES); s.x[1] = take(XBYTES);
     s.sst = take(SSTAGE);
     s.tst = take(TSTAGE);
-    s.sbm = take(RS * 32 * 4);
-    s.state = take(RS * SW * 32 * 4);
-    s.temp = is_default ? s.x + LPAD : take(RS * 16 * 32 * 4);   // default rules: 8 words per lane-word, in place of the input
+    s.sbm[0] = take(RS * 32 * 4); s.sbm[1] = take(RS * 32 * 4);
+    for (int b = 0; b < 2; ++b) s.temp[b] = is_default ? s.x[b] + LPAD : take(RS * TWG * 32 * 4);
     s.per_warp = o - s.warp0;
     s.total = s.warp0 + NW * s.per_warp;
     return s;
@@ -105,45 +113,40 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
     constexpr int NC = kDefault ? 3 : 4;      // split-count planes
     constexpr int NY = kDefault ? 1 : 4;      // sym-count planes
     constexpr int NV = kDefault ? 3 : 5;      // split-value planes
-    constexpr int TWD = kDefault ? 8 : 16;    // temp words per lane-word between pass A and pass C
+    constexpr int TWD = kDefault ? 8 : TWG;   // state words per lane-word
+    constexpr int I_S = kDefault ? 4 : 8, I_H = kDefault ? 5 : 9, I_F = kDefault ? 6 : 10, I_K = kDefault ? 7 : 11, I_E = kDefault ? 3 : 5;
     extern __shared__ __align__(128) unsigned char smem[];
     const Plan sp = plan(p.tl, kDefault);
     uint8_t *tableS = smem + sp.tables;
     Ctl &ctl = *reinterpret_cast<Ctl *>(smem + sp.ctl);
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.mbar);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cw = warp - 1;                  // compute warp number (warp 0, the CTA's oldest warp, is the service warp)
 
     if (ld_volatile_u32(&p.result->error) & 2u) return;  // offsets failed validation in tile_index_kernel
 
-    // ---- one-time per CTA: tables into shared memory, barriers, clean maps, first ticket
+    // ---- one-time per CTA: tables into shared memory, barriers, flags
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.table_blob + p.tl.lutv);
-        const int n16 = (p.tl.total - p.tl.lutv) / 16;
+        const int n16 = (p.tl.stage2 - p.tl.lutv) / 16;
         for (int i = threadIdx.x; i < n16; i += NTH) reinterpret_cast<uint4 *>(tableS)[i] = __ldg(src + i);
-        for (int w = 0; w < NW; ++w) {
-            uint32_t *sbm = reinterpret_cast<uint32_t *>(smem + sp.warp0 + w * sp.per_warp + (sp.sbm - sp.warp0));
-            for (int i = threadIdx.x; i < RS * 32; i += NTH) sbm[i] = 0;
-        }
         if (threadIdx.x == 0) {
-            for (int w = 0; w < NW; ++w) mbar_init(mbar + w, 1);
+            for (int w = 0; w < 2 * NW; ++w) mbar_init(mbar + w, 1);
             for (int w = 0; w <= NW; ++w) { ctl.xch[w] = 0; ctl.xgen[w] = 0; }
-            ctl.tile_id[0] = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base);
+            for (int b = 0; b < 2; ++b) { ctl.tile_id[b] = 0; ctl.tk_cnt[b] = 0; ctl.tk_flag[b] = 0; }
         }
     }
     __syncthreads();
     const bool want_spans = (p.what & 2u) != 0u, want_splits = (p.what & 1u) != 0u;
+    const int ntiles_i = (int)p.ntiles;
 
     // =================================================================================================
-    // service warp: tickets, tile aggregate, look-back, prefix hand-down
+    // service warp: tile aggregate, look-back, prefix hand-down
     // =================================================================================================
-    if (warp == NW) {
+    if (warp == 0) {
         unsigned round = 0;
-        long long tile = ctl.tile_id[0];
-        for (int k = 0; tile < p.ntiles; ++k) {
+        for (int k = 0;; ++k) {
             const int s = k & 1;
-            long long tnext = 0;
-            if (lane == 0) { tnext = (long long)(atomicAdd(p.ticket, 1ull) - p.ticket_base); ctl.tile_id[s ^ 1] = tnext; }
-            tnext = __shfl_sync(FULL, tnext, 0);
             int n = 0, ntok = 0, lft_rel = -1, v = 0; bool irregular = false;
             auto gather = [&]() {
                 nb_sync(BAR_AGG + s, NTH);
@@ -174,6 +177,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 nb_arrive(BAR_PRE + s, NTH);
             };
             gather();
+            const long long tile = ld_vs32(&ctl.tile_id[s]);
+            if (tile >= p.ntiles) break;
             if (irregular) { order_exact(0); gather(); if (lane == 0) atomicAdd(&p.result->prof[15], 1ull); }
             const unsigned ylf = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
             if (lane == 0) {
@@ -203,7 +208,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             }
             __syncwarp();
             nb_arrive(BAR_PRE + s, NTH);
-            tile = tnext;
         }
         return;
     }
@@ -211,18 +215,17 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
     // =================================================================================================
     // compute warps
     // =================================================================================================
-    unsigned char *wbase = smem + sp.warp0 + warp * sp.per_warp;
-    uint8_t *X = wbase + (sp.x - sp.warp0);
+    unsigned char *wbase = smem + sp.warp0 + cw * sp.per_warp;
     uint8_t *sst = wbase + (sp.sst - sp.warp0);
     int2 *tst = reinterpret_cast<int2 *>(wbase + (sp.tst - sp.warp0));
-    uint32_t *sbmS = reinterpret_cast<uint32_t *>(wbase + (sp.sbm - sp.warp0));
-    uint32_t *stateS = reinterpret_cast<uint32_t *>(wbase + (sp.state - sp.warp0));
-    uint32_t *tempS = reinterpret_cast<uint32_t *>(wbase + (sp.temp - sp.warp0));
+    auto Xof = [&](int b) -> uint8_t * { return wbase + (sp.x[b] - sp.warp0); };
+    auto sbmof = [&](int b) -> uint32_t * { return reinterpret_cast<uint32_t *>(wbase + (sp.sbm[b] - sp.warp0)); };
+    auto tempof = [&](int b) -> uint32_t * { return reinterpret_cast<uint32_t *>(wbase + (sp.temp[b] - sp.warp0)); };
     Tables tb;
     tb.ascii_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.ascii_feat - p.tl.lutv));
     tb.class_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.class_feat - p.tl.lutv));
     tb.stage1 = tableS + (p.tl.stage1 - p.tl.lutv);
-    tb.stage2 = tableS + (p.tl.stage2 - p.tl.lutv);
+    tb.stage2 = p.table_blob + p.tl.stage2;
     tb.low_limit = p.tl.low_limit; tb.high_first = p.tl.high_first; tb.high_last = p.tl.high_last; tb.high_feat = p.tl.high_feat;
     const uint32_t *lutv = reinterpret_cast<const uint32_t *>(tableS);
 #ifdef LATOK_PROFILE
@@ -230,8 +233,9 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
 #endif
 
     // ---- window load: TMA bulk copy of the 16-byte aligned interior, plain loads for the ragged end
-    auto begin_load = [&](long long r) -> bool {
+    auto begin_load = [&](long long r, int b) -> bool {
         if (r >= p.nranges) return false;
+        uint8_t *X = Xof(b);
         const long long wl = r * (long long)RANGE - LPAD;          // global position of X[0]
         const long long lo = wl < 0 ? 0 : wl;
         long long hi = wl + XBYTES;
@@ -241,8 +245,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         fence_proxy_async();
         __syncwarp();
         if (lane == 0 && tma_bytes > 0) {
-            mbar_expect_tx(mbar + warp, (uint32_t)tma_bytes);
-            tma_load_1d(X + (lo - wl), p.in + lo, (uint32_t)tma_bytes, mbar + warp);
+            mbar_expect_tx(mbar + 2 * cw + b, (uint32_t)tma_bytes);
+            tma_load_1d(X + (lo - wl), p.in + lo, (uint32_t)tma_bytes, mbar + 2 * cw + b);
         }
         const int a_end = int(lo - wl), b_beg = a_end + tma_bytes;
         for (int i = lane; i < a_end; i += 32) X[i] = 0;
@@ -252,52 +256,66 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         }
         return tma_bytes > 0;
     };
-    auto plain_load = [&](long long r) {          // exact re-analysis: fetch the window again
+    auto plain_load = [&](long long r, int b) {          // exact re-analysis: fetch the window again
+        uint8_t *X = Xof(b);
         const long long wl = r * (long long)RANGE - LPAD;
         for (int i = lane * 16; i < XBYTES; i += 512) {
             const long long g = wl + i;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (g >= 0 && g + 16 <= p.n_bytes) v = *reinterpret_cast<const uint4 *>(p.in + g);
             else if (g + 16 > 0 && g < p.n_bytes) {
-                uint8_t b[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) b[q] = (g + q >= 0 && g + q < p.n_bytes) ? p.in[g + q] : (uint8_t)0;
-                v.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
-                v.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
-                v.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
-                v.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
+                uint32_t w4[4] = {0, 0, 0, 0};
+                for (int q = 0; q < 16; ++q)
+                    if (g + q >= 0 && g + q < p.n_bytes) w4[q >> 2] |= (uint32_t)p.in[g + q] << (8 * (q & 3));
+                v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
             *reinterpret_cast<uint4 *>(X + i) = v;
         }
         __syncwarp();
     };
 
-    // per-range results of the analysis
-    int c_lo = 0, c_hi = 0, n_own = 0, ntok_range = 0, lft = -1, v_out = 0, far = 0;
-    bool closed = true, lo_found = true, irregular = false, last_range = false, have = false;
-    long long w0 = 0, r = 0;
+    // results of the analysis that are posted right away (the rest goes to ctl.rinfo for pass D)
+    int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0; bool a_irregular = false;
 
     // ================================================================================================= analysis
-    auto analyze = [&](bool exact, unsigned round) {
-        c_lo = 0; c_hi = CINF; n_own = 0; ntok_range = 0; lft = -1; v_out = 0; far = 0;
-        closed = true; lo_found = true; irregular = false;
+    auto analyze = [&](const long long r, const int buf, const bool exact, const unsigned round) {
+        const long long w0 = r * (long long)RANGE;
+        const bool have = r < p.nranges, last_range = r == p.nranges - 1;
+        uint8_t *X = Xof(buf);
+        uint32_t *sbmS = sbmof(buf), *tempS = tempof(buf);
+        int c_lo = 0, c_hi = CINF, n_own = 0, ntok_range = 0, lft = -1, v_out = 0, far = 0;
+        bool closed = true, lo_found = true, irregular = false;
+        auto finish = [&]() {
+            a_n_own = n_own; a_ntok = ntok_range; a_lft = lft >= 0 ? lft - c_lo : -1; a_v = v_out; a_irregular = irregular;
+            if (lane == 0) {
+                RInfo &ri = ctl.rinfo[cw][buf];
+                ri.c_lo = c_lo; ri.c_hi = c_hi; ri.n_own = n_own; ri.ntok = ntok_range;
+                ri.flags = (have ? 1 : 0) | (closed ? 2 : 0) | (lo_found ? 4 : 0) | (last_range ? 8 : 0);
+            }
+            __syncwarp();
+        };
         if (!have) {
             if (exact) {      // pass the backlog on
                 int x = 0;
                 if (lane == 0) {
                     unsigned spins = 0;
-                    while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xgen[warp])) != round) { if (++spins > (1u << 26)) break; }
-                    x = ld_vs32(&ctl.xch[warp]);
-                    st_vs32(&ctl.xch[warp + 1], x);
+                    while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xgen[cw])) != round) { if (++spins > (1u << 26)) break; }
+                    x = ld_vs32(&ctl.xch[cw]);
+                    st_vs32(&ctl.xch[cw + 1], x);
                     __threadfence_block();
-                    st_vs32(reinterpret_cast<int *>(&ctl.xgen[warp + 1]), (int)round);
+                    st_vs32(reinterpret_cast<int *>(&ctl.xgen[cw + 1]), (int)round);
                 }
                 v_out = __shfl_sync(FULL, x, 0);
             }
+            c_hi = 0;
+            finish();
             return;
         }
         // ---- string-start map of the window (bit = byte position), from the offsets of the strings that begin in it
         {
+#pragma unroll
+            for (int j = 0; j < RS; ++j) sbmS[j * 32 + lane] = 0;
+            __syncwarp();
             const long long wend = w0 + WIN;
             for (long long s = p.tile_first_str[r] + lane; s <= p.n_strings; s += 32) {
                 const long long o = p.offsets[s];
@@ -345,8 +363,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 const int vhi = rem <= 0 ? 0 : (rem >= 32 ? 32 : int(rem));
                 const uint32_t valid = mask_lt(vhi);
                 const uint32_t sb = sbmS[j * 32 + lane];
-                sbmS[j * 32 + lane] = 0;
                 leadc = (~(b[7] & ~b[6]) & valid) | sb;
+                sbmS[j * 32 + lane] = leadc;                            // from here on the slot holds the lead-byte mask
                 uint32_t mm = b[7] & b[6] & valid;                      // lead bytes of multi-byte characters
                 classify_ascii(b, Pc);
                 while (mm) {
@@ -477,8 +495,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                     const uint32_t ACTf = range_mask(c0, c_lo, CINF) & TRUST;
                     const uint32_t Mm = Mraw & ACTf, CL = CLr & ACTf;
                     uint32_t co;
-                    const uint32_t T0 = chunk_carry(Mm, CL, 0u, co);
-                    (void)T0;
+                    (void)chunk_carry(Mm, CL, 0u, co);
                     const unsigned G = __ballot_sync(FULL, co != 0u), Pg = __ballot_sync(FULL, CL == 0u && co == 0u);
                     const unsigned long long sum = (unsigned long long)(G | Pg) + (unsigned long long)G + (unsigned long long)pend;
                     const uint32_t cin = (((uint32_t)sum ^ Pg) >> lane) & 1u;
@@ -489,22 +506,20 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                     if (js == RS - 1) dup &= range_mask(c0, c_lo, c_hi);
                     dup_any |= dup;
                 }
-                // ---- park the step for pass C
+                // ---- park the step for pass C (in place of its input bytes; step js+1 has been read already)
                 {
                     uint32_t *t = tempS + (js * 32 + lane) * TWD;
-                    const uint32_t pk = pack_ncp(n, c0, (int)((LB >> 3) & 1u));
+                    const uint32_t pk = pack_ncp(n, c0, (int)((LB >> 3) & 1u)) | ((XF & 1u) << 31);
                     if (kDefault) {
                         *reinterpret_cast<uint4 *>(t) = make_uint4(CNT[0], CNT[1], CNT[2], SYC[0]);
-                        *reinterpret_cast<uint4 *>(t + 4) = make_uint4(Sraw, Lm_raw, HOTorM, Fm);
+                        *reinterpret_cast<uint4 *>(t + 4) = make_uint4(Sraw, HOTorM, Fm, pk);
                     } else {
 #pragma unroll
                         for (int q = 0; q < NC; ++q) t[q] = CNT[q];
 #pragma unroll
                         for (int q = 0; q < NY; ++q) t[4 + q] = SYC[q];
-                        t[8] = Sraw; t[9] = Lm_raw; t[10] = HOTorM; t[11] = Fm;
+                        t[I_S] = Sraw; t[I_H] = HOTorM; t[I_F] = Fm; t[I_K] = pk;
                     }
-                    stateS[(js * SW + 5) * 32 + lane] = lead;
-                    stateS[(js * SW + 6) * 32 + lane] = pk;
                 }
             }
 #pragma unroll
@@ -517,14 +532,15 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         if (n_own < 0) n_own = 0;
         if (!exact) {
             irregular = !lo_found || !closed || __any_sync(FULL, dup_any != 0u);
-            if (irregular) return;               // the tile is analysed again by the exact evaluation
+            if (irregular) { finish(); return; }   // the tile is analysed again by the exact evaluation
         }
-        // temp accessors
-        auto T_S = [&](int js) -> uint32_t { return tempS[(js * 32 + lane) * TWD + (kDefault ? 4 : 8)]; };
-        auto T_L = [&](int js) -> uint32_t { return tempS[(js * 32 + lane) * TWD + (kDefault ? 5 : 9)]; };
-        auto T_H = [&](int js) -> uint32_t & { return tempS[(js * 32 + lane) * TWD + (kDefault ? 6 : 10)]; };
-        auto T_F = [&](int js) -> uint32_t { return tempS[(js * 32 + lane) * TWD + (kDefault ? 7 : 11)]; };
-        auto T_K = [&](int js) -> uint32_t { return stateS[(js * SW + 6) * 32 + lane]; };
+        __syncwarp();
+        auto T_at = [&](int js, int w) -> uint32_t & { return tempS[(js * 32 + lane) * TWD + w]; };
+        // character ends its string: the next character (possibly in the next lane-word) starts one
+        auto L_of = [&](uint32_t Fm, uint32_t pk) -> uint32_t {
+            const int n = pk_n(pk);
+            return n > 0 ? ((Fm >> 1) | ((pk >> 31) << (n - 1))) : 0u;
+        };
         auto real_mask = [&](int js, int n) -> uint32_t {
             const long long g0 = w0 + js * STEP + lane * 32;
             const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
@@ -534,7 +550,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             const uint32_t REAL = real_mask(js, n);
             if (closed) return range_mask(c0, c_lo, c_hi) & REAL;
             uint32_t TRUST = REAL;
-            if (js == RS - 1 && lane == 31 && !term_in_win) TRUST &= mask_lt(__popc(stateS[(js * SW + 5) * 32 + lane] & mask_lt(32 - MARGIN)));
+            if (js == RS - 1 && lane == 31 && !term_in_win) TRUST &= mask_lt(__popc(sbmS[js * 32 + lane] & mask_lt(32 - MARGIN)));
             return range_mask(c0, c_lo, CINF) & TRUST;
         };
         // ---------------------------------------------------------------- pass B (exact only): backlog mark by mark
@@ -542,17 +558,18 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             int x = 0;
             if (lane == 0) {
                 unsigned spins = 0;
-                while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xgen[warp])) != round) { if (++spins > (1u << 26)) break; }
-                x = ld_vs32(&ctl.xch[warp]);
+                while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xgen[cw])) != round) { if (++spins > (1u << 26)) break; }
+                x = ld_vs32(&ctl.xch[cw]);
             }
             x = __shfl_sync(FULL, x, 0);
             int v_nom = 0;
 #pragma unroll 1
             for (int js = 0; js < RS; ++js) {
-                const uint32_t pk = T_K(js);
+                const uint32_t pk = T_at(js, I_K);
                 const int n = pk_n(pk), c0 = pk_c0(pk);
                 const uint32_t ACT = act_mask(js, n, c0);
-                const uint32_t S = T_S(js) & ACT, Lm = T_L(js) & ACT, Mm = T_H(js) & ACT, FmA = T_F(js) & ACT;
+                const uint32_t Fr = T_at(js, I_F);
+                const uint32_t S = T_at(js, I_S) & ACT, Lm = L_of(Fr, pk) & ACT, Mm = T_at(js, I_H) & ACT, FmA = Fr & ACT;
                 uint32_t HOT = 0;
                 int xin = 0, out = 0;
                 if (Mm) out = eval_backlog(0, Mm, FmA, S, Lm, HOT);
@@ -565,20 +582,20 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 }
                 x = __shfl_sync(FULL, out, 31);
                 if (js == RS - 1) v_nom = __shfl_sync(FULL, out, 32 - HLANES - 1);
-                T_H(js) = HOT;
+                T_at(js, I_H) = HOT;
             }
             v_out = closed ? x : v_nom;
             if (lane == 0) {
-                st_vs32(&ctl.xch[warp + 1], v_out);
+                st_vs32(&ctl.xch[cw + 1], v_out);
                 __threadfence_block();
-                st_vs32(reinterpret_cast<int *>(&ctl.xgen[warp + 1]), (int)round);
+                st_vs32(reinterpret_cast<int *>(&ctl.xgen[cw + 1]), (int)round);
             }
             // the chunk still open at the end of the trusted halo: hot if a backlog is pending, else look ahead for a mark
             if (!closed) {
-                const uint32_t pk = T_K(RS - 1);
+                const uint32_t pk = T_at(RS - 1, I_K);
                 const int n = pk_n(pk), c0 = pk_c0(pk);
                 const uint32_t ACT = act_mask(RS - 1, n, c0);
-                const uint32_t CL = (T_S(RS - 1) | T_L(RS - 1)) & ACT;
+                const uint32_t CL = (T_at(RS - 1, I_S) | L_of(T_at(RS - 1, I_F), pk)) & ACT;
                 const unsigned H = __ballot_sync(FULL, CL != 0u);
                 const unsigned above = H & (0xFFFFFFFFu << (32 - HLANES));
                 bool nw = false;
@@ -605,24 +622,23 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             int lft_max = -1;
 #pragma unroll 1
             for (int js = RS - 1; js >= 0; --js) {
-                const uint32_t *t = tempS + (js * 32 + lane) * TWD;
-                uint32_t CNT[NC], SYC[NY], Sraw, Lr, HOT, Fm, pk;
+                uint32_t *t = tempS + (js * 32 + lane) * TWD;
+                uint32_t CNT[NC], SYC[NY], Sraw, HOT, Fm, pk;
                 if (kDefault) {
                     const uint4 a = *reinterpret_cast<const uint4 *>(t), b4 = *reinterpret_cast<const uint4 *>(t + 4);
-                    CNT[0] = a.x; CNT[1] = a.y; CNT[2] = a.z; SYC[0] = a.w; Sraw = b4.x; Lr = b4.y; HOT = b4.z; Fm = b4.w;
+                    CNT[0] = a.x; CNT[1] = a.y; CNT[2] = a.z; SYC[0] = a.w; Sraw = b4.x; HOT = b4.y; Fm = b4.z; pk = b4.w;
                 } else {
 #pragma unroll
                     for (int q = 0; q < NC; ++q) CNT[q] = t[q];
 #pragma unroll
                     for (int q = 0; q < NY; ++q) SYC[q] = t[4 + q];
-                    Sraw = t[8]; Lr = t[9]; HOT = t[10]; Fm = t[11];
+                    Sraw = t[I_S]; HOT = t[I_H]; Fm = t[I_F]; pk = t[I_K];
                 }
-                pk = stateS[(js * SW + 6) * 32 + lane];
                 const int n = pk_n(pk), c0 = pk_c0(pk);
                 const uint32_t REAL = real_mask(js, n);
                 const uint32_t OWN = range_mask(c0, c_lo, c_hi) & REAL;
                 const uint32_t ACT = closed ? OWN : act_mask(js, n, c0);
-                const uint32_t CL = (Sraw | Lr) & ACT;
+                const uint32_t CL = (Sraw | L_of(Fm, pk)) & ACT;
                 HOT &= CL;
                 const bool hasCL = CL != 0u;
                 const bool firstHot = hasCL && (HOT & (CL & (0u - CL))) != 0u;
@@ -668,25 +684,35 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 const uint32_t SPq = SPLIT & mask_lt(n) & range_mask(c0, c_lo, closed ? c_hi + 1 : c_hi);
                 const unsigned hs = __ballot_sync(FULL, SPq != 0u);
                 const int firstsp = __shfl_sync(FULL, c0 + __ffs(SPq) - 1, hs ? __ffs(hs) - 1 : 0);
-                if (lane == 0) { ctl.tokstep[warp][js] = tot; ctl.nsa[warp][js] = nsa_carry; }
+                if (lane == 0) { ctl.tokstep[cw][buf][js] = tot; ctl.nsa[cw][buf][js] = nsa_carry; }
                 if (hs) nsa_carry = firstsp;
                 const uint32_t FO = Fm & OWN;
                 if (FO) lft_max = max(lft_max, c0 + 31 - __clz(FO));
-                // state for pass D
-                uint32_t *st = stateS + js * SW * 32 + lane;
-                st[0] = V[0]; st[32] = V[1]; st[64] = V[2]; st[96] = E; st[128] = Fm;
-                st[192] = (pk & 0xC007FFFFu) | ((uint32_t)(ts - mytok) << 19);
-                if (!kDefault) { uint32_t *t2 = tempS + (js * 32 + lane) * TWD; t2[13] = V[3]; t2[14] = V[4]; }
+                // state for pass D, in place
+                const uint32_t pk2 = (pk & 0xC007FFFFu) | ((uint32_t)(ts - mytok) << 19);
+                if (kDefault) {
+                    *reinterpret_cast<uint4 *>(t) = make_uint4(V[0], V[1], V[2], E);
+                    t[I_K] = pk2;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) t[q] = V[q];
+                    t[I_E] = E; t[I_K] = pk2;
+                }
             }
             lft = __reduce_max_sync(FULL, lft_max);
-            __syncwarp();
         }
+        finish();
         PROF5(3);
     };
 
     // ================================================================================================= output
-    auto output = [&](unsigned long long G_in, unsigned long long K_in, unsigned long long base_in, bool direct_spans) {
+    auto output = [&](const long long r, const int buf, unsigned long long G_in, unsigned long long K_in, unsigned long long base_in, bool direct_spans) {
+        const RInfo ri = ctl.rinfo[cw][buf];
+        const bool have = (ri.flags & 1) != 0, closed = (ri.flags & 2) != 0, lo_found = (ri.flags & 4) != 0, last_range = (ri.flags & 8) != 0;
         if (!have) return;
+        const int c_lo = ri.c_lo, c_hi = ri.c_hi, n_own = ri.n_own, ntok_range = ri.ntok;
+        const long long w0 = r * (long long)RANGE;
+        const uint32_t *tempS = tempof(buf), *leadS = sbmof(buf);
         if (K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens && lane == 0) atomicOr(&p.result->error, 4u);
         if (G_in + (unsigned long long)n_own > (unsigned long long)p.n_bytes || K_in + (unsigned long long)ntok_range > (unsigned long long)p.n_bytes + 1ull) {
             if (lane == 0 && atomicOr(&p.result->error, 8u) == 0u) {
@@ -704,11 +730,17 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         const bool spans_direct_all = direct_spans || !closed || !lo_found;
 #pragma unroll 1
         for (int js = 0; js < RS; ++js) {
-            const uint32_t *st = stateS + js * SW * 32 + lane;
-            uint32_t V[NV];
-            V[0] = st[0]; V[1] = st[32]; V[2] = st[64];
-            if (!kDefault) { const uint32_t *t2 = tempS + (js * 32 + lane) * TWD; V[3] = t2[13]; V[4] = t2[14]; }
-            const uint32_t E = st[96], Fm = st[128], lead = st[160], pk = st[192];
+            const uint32_t *t = tempS + (js * 32 + lane) * TWD;
+            uint32_t V[NV], E, Sraw, Fm, pk;
+            if (kDefault) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(t), b4 = *reinterpret_cast<const uint4 *>(t + 4);
+                V[0] = a.x; V[1] = a.y; V[2] = a.z; E = a.w; Sraw = b4.x; Fm = b4.z; pk = b4.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < NV; ++q) V[q] = t[q];
+                E = t[I_E]; Sraw = t[I_S]; Fm = t[I_F]; pk = t[I_K];
+            }
+            const uint32_t lead = leadS[js * 32 + lane];
             const int n = pk_n(pk), c0 = pk_c0(pk), tp = pk_tp(pk);
             const long long g0 = w0 + js * STEP + lane * 32;
             const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
@@ -717,7 +749,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             const int cstep0 = __shfl_sync(FULL, c0, 0), cstep1 = __shfl_sync(FULL, c0 + n, 31);
             const int cf = max(c_lo, cstep0), cend = min(c_hi, cstep1);     // owned characters of this step: [cf, cend)
             const int nb = cend - cf;
-            const int ntok_step = ctl.tokstep[warp][js];
+            const int ntok_step = ctl.tokstep[cw][buf][js];
             uint32_t SPLIT = 0;
 #pragma unroll
             for (int q = 0; q < NV; ++q) SPLIT |= V[q];
@@ -831,7 +863,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 {
                     const unsigned above = lane == 31 ? 0u : (hs & (0xFFFFFFFFu << (lane + 1)));
                     const int got = __shfl_sync(FULL, myfirst, above ? __ffs(above) - 1 : 0);
-                    nextsplit = above ? got : ctl.nsa[warp][js];
+                    nextsplit = above ? got : ctl.nsa[cw][buf][js];
                 }
                 uint32_t ev = E;
                 int rank = 0;
@@ -855,9 +887,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                     ++rank;
                 }
                 // a range whose head is not chunk-aligned: its first split that follows a non-space character ends the
-                // token left open by earlier ranges (exact evaluation only; the temp words are still in place)
+                // token left open by earlier ranges
                 if (!lo_found && r > 0) {
-                    const uint32_t Sraw = tempS[(js * 32 + lane) * TWD + (kDefault ? 4 : 8)];
                     const uint32_t PSr = (Sraw << 1) | pk_ps(pk);
                     const uint32_t END = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo, last_range ? c_hi + 1 : c_hi);
                     if (END) {
@@ -918,39 +949,57 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
     };
 
     // ================================================================================================= main loop
-    unsigned xphase = 0, round = 0;
-    long long tile = ctl.tile_id[0];
-    bool tma_pending = false;
-    if (tile < p.ntiles) tma_pending = begin_load(tile * NW + warp);
-    for (int k = 0; tile < p.ntiles; ++k) {
+    // ticket of iteration k (slot k & 1): taken by the first warp that gets here, the others read it
+    auto next_tile = [&](int k) -> int {
         const int s = k & 1;
-        r = tile * NW + warp; w0 = r * (long long)RANGE;
-        have = r < p.nranges; last_range = r == p.nranges - 1;
-        if (tma_pending) {
-            unsigned spins = 0;
-            while (!mbar_try_wait(mbar + warp, xphase)) {
-                if (++spins > (1u << 24)) { if (lane == 0) atomicOr(&p.result->error, 1u); break; }   // watchdog: never hang the device
+        int t = 0;
+        if (lane == 0) {
+            const int old = atomicAdd(&ctl.tk_cnt[s], 1);
+            if (old == NW - 1) st_vs32(&ctl.tk_cnt[s], 0);       // everybody has been here: ready for iteration k + 2
+            if (old == 0) {
+                const unsigned long long tk = atomicAdd(p.ticket, 1ull) - p.ticket_base;
+                t = tk < (unsigned long long)ntiles_i ? (int)tk : ntiles_i;
+                st_vs32(&ctl.tile_id[s], t);
+                __threadfence_block();
+                st_vs32(&ctl.tk_flag[s], k + 1);
+            } else {
+                unsigned spins = 0;
+                while (ld_vs32(&ctl.tk_flag[s]) != k + 1) { if (++spins > (1u << 26)) { atomicOr(&p.result->error, 1u); break; } }
+                t = ld_vs32(&ctl.tile_id[s]);
             }
-            xphase ^= 1u;
+        }
+        return __shfl_sync(FULL, t, 0);
+    };
+    auto post = [&](int s) {
+        if (lane == 0) {
+            WAgg &a = ctl.wagg[s][cw];
+            a.n_own = a_n_own; a.ntok = a_ntok; a.lft = a_lft; a.v = a_v; a.flags = a_irregular ? 1 : 0;
+            __threadfence_block();
         }
         __syncwarp();
-        PROF5(0);
-        analyze(false, 0u);
+        nb_arrive(BAR_AGG + s, NTH);
+    };
+    auto wait_window = [&](int b, unsigned &phase_bits) {
+        unsigned spins = 0;
+        while (!mbar_try_wait(mbar + 2 * cw + b, (phase_bits >> b) & 1u)) {
+            if (++spins > (1u << 24)) { if (lane == 0) atomicOr(&p.result->error, 1u); break; }   // watchdog: never hang the device
+        }
+        phase_bits ^= 1u << b;
+    };
+    // write out tile `tile` (iteration kk): wait for its prefix (running the exact evaluation if asked to), then pass D
+    unsigned round = 0;
+    auto finish_tile = [&](int tile, int kk) {
+        const int s = kk & 1;
+        const long long r = (long long)tile * NW + cw;
         bool exact_done = false;
         for (;;) {
-            if (lane == 0) {
-                WAgg &a = ctl.wagg[s][warp];
-                a.n_own = n_own; a.ntok = ntok_range; a.lft = lft >= 0 ? lft - c_lo : -1; a.v = v_out; a.flags = irregular ? 1 : 0;
-                __threadfence_block();
-            }
-            __syncwarp();
-            nb_arrive(BAR_AGG + s, NTH);
             nb_sync(BAR_PRE + s, NTH);
             if (ctl.slot[s].mode == 0) break;
             ++round;
-            if (have) plain_load(r);
-            analyze(true, round);
+            if (r < p.nranges) plain_load(r, s);
+            analyze(r, s, true, round);
             exact_done = true;
+            post(s);
         }
         PROF5(4);
         // own prefix: the tile's plus the ranges before this one
@@ -958,8 +1007,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         {
             const Slot sl = ctl.slot[s];
             const WAgg a = ctl.wagg[s][lane < NW ? lane : 0];
-            const bool before = lane < warp;
-            const int pn = __reduce_add_sync(FULL, before ? a.n_own : 0), pk = __reduce_add_sync(FULL, before ? a.ntok : 0);
+            const bool before = lane < cw;
+            const int pn = __reduce_add_sync(FULL, before ? a.n_own : 0), pkk = __reduce_add_sync(FULL, before ? a.ntok : 0);
             int pnx = lane < NW ? a.n_own : 0;            // exclusive prefix of characters per range
             {
                 int inc = pnx;
@@ -969,19 +1018,35 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             }
             const unsigned hl = __ballot_sync(FULL, before && a.lft >= 0);
             const int lv = __shfl_sync(FULL, pnx + a.lft, hl ? 31 - __clz(hl) : 0);
-            G_in = sl.G + (unsigned long long)pn; K_in = sl.K + (unsigned long long)pk;
+            G_in = sl.G + (unsigned long long)pn; K_in = sl.K + (unsigned long long)pkk;
             base_in = hl ? sl.G + (unsigned long long)lv : sl.base;
         }
-        const long long tnext = ctl.tile_id[s ^ 1];
-        tma_pending = false;
-        // the next window is fetched while this one is written out (the exact path still reads the temp words that live
-        // in the window buffer, so there it waits)
-        const bool early = kDefault && !exact_done;
-        if (tnext < p.ntiles && early) tma_pending = begin_load(tnext * NW + warp);
-        output(G_in, K_in, base_in, exact_done);
-        if (tnext < p.ntiles && !early) tma_pending = begin_load(tnext * NW + warp);
+        output(r, s, G_in, K_in, base_in, exact_done);
         PROF5(5);
-        tile = tnext;
+    };
+
+    unsigned phase_bits = 0;
+    bool pending[2] = {false, false};
+    int tile_cur = next_tile(0), tile_prev = -1;
+    if (tile_cur < ntiles_i) pending[0] = begin_load((long long)tile_cur * NW + cw, 0);
+    for (int k = 0;; ++k) {
+        const int s = k & 1;
+        if (tile_cur < ntiles_i) {
+            if (s == 0 ? pending[0] : pending[1]) wait_window(s, phase_bits);
+            __syncwarp();
+            PROF5(0);
+            analyze((long long)tile_cur * NW + cw, s, false, 0u);
+            post(s);
+        } else {
+            nb_arrive(BAR_AGG + s, NTH);                 // tells the service warp that the tickets have run out
+        }
+        if (tile_prev >= 0) finish_tile(tile_prev, k - 1);
+        if (tile_cur >= ntiles_i) break;
+        const int tile_next = next_tile(k + 1);
+        bool pn = false;
+        if (tile_next < ntiles_i) pn = begin_load((long long)tile_next * NW + cw, s ^ 1);
+        if (s == 0) pending[1] = pn; else pending[0] = pn;
+        tile_prev = tile_cur; tile_cur = tile_next;
     }
 }
 
