@@ -16,6 +16,7 @@ constexpr unsigned SPIN_LIMIT = 1u << 23; // watchdog for look-back spins
 
 // ---- small helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mask_lt(int k) { return __funnelshift_lc(0xFFFFFFFFu, 0u, (unsigned)max(k, 0)); }  // low k bits (k clamped to 0..32)
+__device__ __forceinline__ uint32_t mask_lt_nn(int k) { return __funnelshift_lc(0xFFFFFFFFu, 0u, (unsigned)k); }       // same, k known to be >= 0
 // bits of a thread's 32-character word that fall inside the character range [lo, hi)
 __device__ __forceinline__ uint32_t range_mask(int base, int lo, int hi)
 {

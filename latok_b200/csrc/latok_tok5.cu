@@ -326,8 +326,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             __syncwarp();
         }
         // ---- the character in front of the window (prev-context of the first character)
+        // (only matters when the range owns its very first character, i.e. no closer was found in the head window: such a
+        // range is irregular and comes back here with exact = true)
         uint32_t prevLB = 0;
-        if (w0 > 0) {
+        if (exact && w0 > 0) {
             const uint8_t *q = X + LPAD - 1;
             int back = 0;
             while (back < 3 && (q[-back] & 0xC0u) == 0x80u) ++back;
@@ -335,6 +337,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             prevLB = (w & 1u) | (((w >> 1) & 1u) << 1) | (((w >> 3) & 1u) << 2) | (((w >> 5) & 1u) << 3) | (((w >> 6) & 1u) << 4);
         }
         const bool term_in_win = p.n_bytes < w0 + WIN;
+        const long long rem64 = p.n_bytes - w0;
+        const int nb_win = rem64 > (long long)(WIN + 64) ? WIN + 64 : (int)rem64;      // data bytes from the window start on (clamped)
         const int jt = last_range ? int((p.n_bytes - w0) >> 10) : -1;       // step / lane / bit of the end of the data
         const int lt = last_range ? int(((p.n_bytes - w0) >> 5) & 31) : 0, bt = last_range ? int((p.n_bytes - w0) & 31) : 0;
 
@@ -358,10 +362,9 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 const uint32_t wds[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
                 uint32_t b[8];
                 bytes_to_planes(wds, b);
-                const long long g0 = w0 + j * STEP + lane * 32;
-                const long long rem = p.n_bytes - g0;
-                const int vhi = rem <= 0 ? 0 : (rem >= 32 ? 32 : int(rem));
-                const uint32_t valid = mask_lt(vhi);
+                const int rem = nb_win - (j * STEP + lane * 32);
+                const int vhi = min(max(rem, 0), 32);
+                const uint32_t valid = mask_lt_nn(vhi);
                 const uint32_t sb = sbmS[j * 32 + lane];
                 leadc = (~(b[7] & ~b[6]) & valid) | sb;
                 sbmS[j * 32 + lane] = leadc;                            // from here on the slot holds the lead-byte mask
@@ -402,11 +405,11 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 const uint32_t XLO = __shfl_sync(FULL, lane == 0 ? Pc[PL_LO] : P[PL_LO], nl), XSP = __shfl_sync(FULL, lane == 0 ? Pc[PL_SP] : P[PL_SP], nl);
                 const uint32_t XAT = __shfl_sync(FULL, lane == 0 ? Pc[PL_AT] : P[PL_AT], nl), XSL = __shfl_sync(FULL, lane == 0 ? Pc[PL_SL] : P[PL_SL], nl);
                 const uint32_t XF = __shfl_sync(FULL, lane == 0 ? Fc : Fm, nl);
-                const long long g0 = w0 + js * STEP + lane * 32;
-                const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
+                const unsigned trel = (unsigned)(nb_win - (js * STEP + lane * 32));
+                const bool has_term = trel < 32u;                 // the end-of-data terminator is this lane-word's last character
                 const uint32_t REAL = mask_lt(n - (has_term ? 1 : 0));
                 uint32_t TRUST = REAL;
-                if (js == RS - 1 && lane == 31 && !term_in_win) TRUST &= mask_lt(__popc(lead & mask_lt(32 - MARGIN)));
+                if (js == RS - 1 && lane == 31 && !term_in_win) TRUST &= mask_lt_nn(__popc(lead & mask_lt_nn(32 - MARGIN)));
                 auto next1 = [&](uint32_t Xc, uint32_t Xn) -> uint32_t {
                     const uint32_t l = Xc | __funnelshift_lc(0u, Xn, n), h = __funnelshift_lc(Xn, 0u, n);
                     return __funnelshift_r(l, h, 1);
@@ -542,8 +545,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             return n > 0 ? ((Fm >> 1) | ((pk >> 31) << (n - 1))) : 0u;
         };
         auto real_mask = [&](int js, int n) -> uint32_t {
-            const long long g0 = w0 + js * STEP + lane * 32;
-            const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
+            const bool has_term = (unsigned)(nb_win - (js * STEP + lane * 32)) < 32u;
             return mask_lt(n - (has_term ? 1 : 0));
         };
         auto act_mask = [&](int js, int n, int c0) -> uint32_t {
@@ -712,6 +714,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         if (!have) return;
         const int c_lo = ri.c_lo, c_hi = ri.c_hi, n_own = ri.n_own, ntok_range = ri.ntok;
         const long long w0 = r * (long long)RANGE;
+        const long long rem64 = p.n_bytes - w0;
+        const int nb_win = rem64 > (long long)(WIN + 64) ? WIN + 64 : (int)rem64;
         const uint32_t *tempS = tempof(buf), *leadS = sbmof(buf);
         if (K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens && lane == 0) atomicOr(&p.result->error, 4u);
         if (G_in + (unsigned long long)n_own > (unsigned long long)p.n_bytes || K_in + (unsigned long long)ntok_range > (unsigned long long)p.n_bytes + 1ull) {
@@ -725,7 +729,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         // range-relative character index of the first character of the string that is open at c_lo (may be negative)
         int cur_base = c_lo - (int)(long long)(G_in - base_in);
         int ktok = 0;                      // tokens of the range before this step
-        long long qn = p.tile_first_str[r];
         uint32_t prev_tailw = 0;
         const bool spans_direct_all = direct_spans || !closed || !lo_found;
 #pragma unroll 1
@@ -742,8 +745,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             }
             const uint32_t lead = leadS[js * 32 + lane];
             const int n = pk_n(pk), c0 = pk_c0(pk), tp = pk_tp(pk);
-            const long long g0 = w0 + js * STEP + lane * 32;
-            const bool has_term = p.n_bytes >= g0 && p.n_bytes < g0 + 32;
+            const int wrel = nb_win - (js * STEP + lane * 32);          // data bytes from this lane-word on
+            const bool has_term = (unsigned)wrel < 32u;
             const uint32_t REAL = mask_lt(n - (has_term ? 1 : 0));
             const uint32_t OWN = range_mask(c0, c_lo, c_hi) & REAL;
             const int cstep0 = __shfl_sync(FULL, c0, 0), cstep1 = __shfl_sync(FULL, c0 + n, 31);
@@ -787,40 +790,40 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 }
                 uint32_t headw = __shfl_up_sync(FULL, tailw, 1);
                 if (lane == 0) headw = prev_tailw;
-                const long long gfull = p.n_bytes - g0;
-                const bool slow = __any_sync(FULL, gfull >= 32 && n < 4);       // malformed UTF-8 only
+                const bool slow = __any_sync(FULL, wrel >= 32 && n < 4);       // malformed UTF-8 only
                 const int o = SPAD + a + (c0 - cf);                 // staging offset of this lane's first character
-                if (o >= 4 && n > 0) {
-                    if (!slow) {
-                        // words are written by the lane that owns their LAST byte: no partial words, no races
-                        const int s = o & 3;
-                        const int cnt = (s + n) >> 2;
-                        uint32_t *dst = reinterpret_cast<uint32_t *>(sst) + (o >> 2);
-                        const int sh = 32 - 8 * s;
-                        uint32_t prev = headw;
+                const bool act = o >= 4 && n > 0;
+                if (!slow) {
+                    // words are written by the lane that owns their LAST byte: no partial words, no races
+                    const int s = o & 3;
+                    const int cnt = (s + n) >> 2;
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(sst) + (o >> 2);
+                    const int sh = 32 - 8 * s;
+                    uint32_t prev = headw;
+                    uint32_t Wo[9];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const uint32_t w = s ? __funnelshift_r(prev, W[i], sh) : W[i];
-                            if (i < cnt) dst[i] = w;
-                            prev = W[i];
-                        }
-                        if (8 < cnt) dst[8] = __funnelshift_r(prev, 0u, sh);
-                        // the lane that holds the last owned character of the step flushes the trailing partial word
-                        if (c0 < cend && c0 + n >= cend) {
-                            const int end = SPAD + a + nb;
-                            for (int q = end & ~3; q < end; ++q) {
-                                const int jj = q - o;
-                                const uint32_t srcw = jj >= 0 ? W[jj >> 2] >> ((jj & 3) * 8) : headw >> ((4 + jj) * 8);
-                                sst[q] = (uint8_t)(srcw & 0xFFu);
-                            }
-                        }
-                    } else {
-                        for (int jj = 0; jj < n; ++jj) {
-                            uint32_t vv = 0;
+                    for (int i = 0; i < 8; ++i) { Wo[i] = s ? __funnelshift_r(prev, W[i], sh) : W[i]; prev = W[i]; }
+                    Wo[8] = __funnelshift_r(prev, 0u, sh);
+                    // first the word that holds this lane's trailing bytes (its upper bytes belong to the next lane, which
+                    // overwrites the whole word below), then, after the warp has re-converged, the full words
+                    if (act && ((s + n) & 3) != 0) {
+                        uint32_t tw = Wo[8];
 #pragma unroll
-                            for (int q = 0; q < NV; ++q) vv |= ((V[q] >> jj) & 1u) << q;
-                            sst[o + jj] = (uint8_t)vv;
-                        }
+                        for (int i = 0; i < 8; ++i) if (i == cnt) tw = Wo[i];
+                        dst[cnt] = tw;
+                    }
+                    __syncwarp();
+                    if (act) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) if (i < cnt) dst[i] = Wo[i];
+                        if (8 < cnt) dst[8] = Wo[8];
+                    }
+                } else if (act) {
+                    for (int jj = 0; jj < n; ++jj) {
+                        uint32_t vv = 0;
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) vv |= ((V[q] >> jj) & 1u) << q;
+                        sst[o + jj] = (uint8_t)vv;
                     }
                 }
                 prev_tailw = __shfl_sync(FULL, tailw, 31);
@@ -865,6 +868,27 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                     const int got = __shfl_sync(FULL, myfirst, above ? __ffs(above) - 1 : 0);
                     nextsplit = above ? got : ctl.nsa[cw][buf][js];
                 }
+                const bool multi_f = __any_sync(FULL, (FO & (FO - 1u)) != 0u);      // two string starts inside one lane-word
+                if (!direct && !multi_f) {
+                    // bit-reversed planes: __clz walks the tokens in ascending order, the first split after a token is the
+                    // highest bit below it.  At most one string start per lane-word here.
+                    uint32_t evr = __brev(E);
+                    const uint32_t spr = __brev(SPq), e2r = __brev(E & ~SPLIT);     // e2r: the span began one character earlier
+                    const int fpos = FO ? 31 - __clz(FO) : 64;
+                    const int offA = c0 - lf_excl;                                   // index = position in the lane-word + off
+                    const int nse = nextsplit >= 0 ? nextsplit - c0 : -(1 << 28);
+                    int2 *dp = tst + ka + tp;
+                    while (evr) {
+                        const int i = __clz(evr);
+                        const uint32_t bit = 0x80000000u >> i;
+                        evr ^= bit;
+                        const int off = i >= fpos ? -fpos : offA;
+                        const int e = __clz(spr & (bit - 1u));
+                        const int sidx = i + off - ((e2r & bit) ? 1 : 0);
+                        const int eidx = (e < 32 ? e : nse) + off;
+                        *dp++ = make_int2(sidx, eidx);
+                    }
+                } else {
                 uint32_t ev = E;
                 int rank = 0;
                 int cbase = lf_excl;
@@ -885,6 +909,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                         }
                     }
                     ++rank;
+                }
                 }
                 // a range whose head is not chunk-aligned: its first split that follows a non-space character ends the
                 // token left open by earlier ranges
@@ -916,31 +941,33 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                     __syncwarp();
                 }
             }
-            // ------------------------------------------------------------ CSR offsets of the strings that start in this step
-            {
-                const long long sbeg = w0 + (long long)js * STEP, send = sbeg + STEP;
-                for (;;) {
-                    const long long q = qn + lane;
-                    const long long o = q <= p.n_strings ? p.offsets[q] : 0x7FFFFFFFFFFFFFFFLL;
-                    const bool in = o < send;
-                    const int wb = in ? int(o - sbeg) : 0;
-                    const int tl = (wb >> 5) & 31;
-                    const uint32_t l_lead = __shfl_sync(FULL, lead, tl), l_E = __shfl_sync(FULL, E, tl);
-                    const int l_c0 = __shfl_sync(FULL, c0, tl), l_tp = __shfl_sync(FULL, tp, tl);
-                    if (in) {
-                        const int c = l_c0 + __popc(l_lead & mask_lt(wb & 31));
-                        const bool mine = last_range ? (c >= c_lo) : (c >= c_lo && c < c_hi);
-                        if (mine) {
-                            p.char_off[q] = (long long)(G_in + (unsigned long long)(c - c_lo));
-                            p.tok_off[q] = (long long)K_in + ktok + l_tp + __popc(l_E & mask_lt(c - l_c0));
-                        }
-                    }
-                    const int cnt = __popc(__ballot_sync(FULL, in));
-                    qn += cnt;
-                    if (cnt < 32) break;
-                }
-            }
             ktok += ntok_step;
+        }
+        // ---------------------------------------------------------------- CSR offsets of the strings that start in this range
+        // (one lane per string; the character / token counts in front of a byte position come from the parked state)
+        {
+            __syncwarp();
+            const long long wend = w0 + WIN;
+            for (long long q = p.tile_first_str[r] + lane;; q += 32) {
+                const long long o = q <= p.n_strings ? p.offsets[q] : 0x7FFFFFFFFFFFFFFFLL;
+                const bool in = o < wend;
+                if (in) {
+                    const int wb = int(o - w0);
+                    const int js = wb >> 10, tl = (wb >> 5) & 31;
+                    const uint32_t *t = tempS + (js * 32 + tl) * TWD;
+                    const uint32_t l_pk = t[I_K], l_E = t[I_E], l_lead = leadS[js * 32 + tl];
+                    const int l_c0 = pk_c0(l_pk);
+                    const int c = l_c0 + __popc(l_lead & mask_lt_nn(wb & 31));
+                    const bool mine = last_range ? (c >= c_lo) : (c >= c_lo && c < c_hi);
+                    if (mine) {
+                        int kb = 0;
+                        for (int q2 = 0; q2 < js; ++q2) kb += ctl.tokstep[cw][buf][q2];
+                        p.char_off[q] = (long long)(G_in + (unsigned long long)(c - c_lo));
+                        p.tok_off[q] = (long long)K_in + kb + pk_tp(l_pk) + __popc(l_E & mask_lt(c - l_c0));
+                    }
+                }
+                if (!__all_sync(FULL, in)) break;
+            }
         }
         if (last_range && lane == 0) {
             p.result->n_chars = G_in + (unsigned long long)n_own;
