@@ -367,7 +367,7 @@ def main():
                 "steps": e2e_steps, "strings_per_s": world * S0 * e2e_steps / e2e_s},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "latok::tokenize_kernel", "kernel_ms": k_ms,
+                     "traffic": traffic, "kernel": "latok::v5::tokenize5_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": float(alg), "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": sampler.summary(),

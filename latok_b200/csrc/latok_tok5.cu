@@ -179,15 +179,24 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             gather();
             const long long tile = ld_vs32(&ctl.tile_id[s]);
             if (tile >= p.ntiles) break;
-            if (irregular) { order_exact(0); gather(); if (lane == 0) atomicAdd(&p.result->prof[15], 1ull); }
-            const unsigned ylf = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
-            if (lane == 0) {
-                uint4 r;
-                r.x = (p.epoch << 2) | 1u; r.y = ylf; r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
-                st_rec(p.agg + tile, r);
+            Prefix pre;
+            if (irregular) {
+                // the fast evaluation does not apply (a chunk with several marks, or one that is open at a range boundary):
+                // take the exact prefix first, then evaluate once with the backlog that really enters; nothing is published
+                // for this tile until then, so the tiles after it wait
+                pre = lookback(tile, p, lane);
+                order_exact(pre.x); gather();
+                if (lane == 0) atomicAdd(&p.result->prof[15], 1ull);
+            } else {
+                const unsigned ylf = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
+                if (lane == 0) {
+                    uint4 r;
+                    r.x = (p.epoch << 2) | 1u; r.y = ylf; r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
+                    st_rec(p.agg + tile, r);
+                }
+                pre = lookback(tile, p, lane);
+                if (pre.x != 0) { order_exact(pre.x); gather(); }
             }
-            const Prefix pre = lookback(tile, p, lane);
-            if (pre.x != 0) { order_exact(pre.x); gather(); }
             if (lane == 0) {
                 IncRec *ir = p.inc + tile;
                 uint4 a, bq;
@@ -274,6 +283,36 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         __syncwarp();
     };
 
+    // Exact block-mask forward pass over one step (latok.c:218-244 in scan form): every lane-word becomes a backlog
+    // transfer function x -> max(x + u, v) (string start = reset, mark = +1, space = one off but not below 0, end of
+    // string = reset), a warp scan composes them, then each lane walks its own events once with the backlog that
+    // really enters it.  Returns the hot closers; `x` is the backlog entering the step, `out` leaves this lane-word.
+    auto exact_step = [&](int x, uint32_t Mm, uint32_t FmA, uint32_t S, uint32_t Lm, int &out) -> uint32_t {
+        Fn f = fn_id();
+        {
+            uint32_t evs = Mm | FmA | S | Lm;
+            while (evs) {
+                const uint32_t b = evs & (0u - evs); evs ^= b;
+                if (FmA & b) f = fn_compose(f, Fn{NEG, 0});
+                if (Mm & b) f = fn_compose(f, Fn{1, NEG});
+                if (S & b) f = fn_compose(f, Fn{-1, 0});
+                if (Lm & b) f = fn_compose(f, Fn{NEG, 0});
+            }
+        }
+        Fn inc = f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int ou = __shfl_up_sync(FULL, inc.u, d), ov = __shfl_up_sync(FULL, inc.v, d);
+            if (lane >= d) inc = fn_compose(Fn{ou, ov}, inc);
+        }
+        const int eu = __shfl_up_sync(FULL, inc.u, 1), ev2 = __shfl_up_sync(FULL, inc.v, 1);
+        const int xin = lane ? fn_apply(Fn{eu, ev2}, x) : x;
+        uint32_t HOT = 0;
+        out = xin;
+        if (xin != 0 || Mm) out = eval_backlog(xin, Mm, FmA, S, Lm, HOT);
+        return HOT;
+    };
+
     // results of the analysis that are posted right away (the rest goes to ctl.rinfo for pass D)
     int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0; bool a_irregular = false;
 
@@ -347,8 +386,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
 #pragma unroll
         for (int f = 0; f < NBASE; ++f) Pp[f] = 0;
         int crun = 0;                    // characters of the range so far
-        uint32_t pend = 0;               // fast block mask: a mark is pending in the open chunk
-        uint32_t dup_any = 0;
+        int xb = 0;                      // block-mask backlog entering the next step (fast evaluation: 0 or 1 mark pending)
 
 #pragma unroll 1
         for (int j = 0; j <= RS; ++j) {
@@ -495,19 +533,24 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 // ---- forward half of the block mask, common case: a carry-propagating add per lane-word
                 uint32_t HOTorM = Mraw;
                 if (!exact) {
-                    const uint32_t ACTf = range_mask(c0, c_lo, CINF) & TRUST;
+                    // characters the block mask runs over: the owned ones (c_hi is still "infinite" before the last step)
+                    const uint32_t ACTf = range_mask(c0, c_lo, c_hi) & TRUST;
                     const uint32_t Mm = Mraw & ACTf, CL = CLr & ACTf;
                     uint32_t co;
                     (void)chunk_carry(Mm, CL, 0u, co);
                     const unsigned G = __ballot_sync(FULL, co != 0u), Pg = __ballot_sync(FULL, CL == 0u && co == 0u);
-                    const unsigned long long sum = (unsigned long long)(G | Pg) + (unsigned long long)G + (unsigned long long)pend;
+                    const unsigned long long sum = (unsigned long long)(G | Pg) + (unsigned long long)G + (unsigned long long)(xb != 0 ? 1u : 0u);
                     const uint32_t cin = (((uint32_t)sum ^ Pg) >> lane) & 1u;
-                    pend = (uint32_t)(sum >> 32) & 1u;
                     const uint32_t T = chunk_carry(Mm, CL, cin, co);
-                    HOTorM = T & CL;
-                    uint32_t dup = Mm & ~CL & T;
-                    if (js == RS - 1) dup &= range_mask(c0, c_lo, c_hi);
-                    dup_any |= dup;
+                    if (xb < 2 && !__any_sync(FULL, (Mm & ~CL & T) != 0u)) {
+                        HOTorM = T & CL;
+                        xb = (int)((sum >> 32) & 1u);
+                    } else {
+                        // a chunk with several marks (or a backlog of several): this step mark by mark
+                        int out;
+                        HOTorM = exact_step(xb, Mm, Fm & ACTf, Sraw & ACTf, Lm_raw & ACTf, out);
+                        xb = __shfl_sync(FULL, out, 31);
+                    }
                 }
                 // ---- park the step for pass C (in place of its input bytes; step js+1 has been read already)
                 {
@@ -534,8 +577,16 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         n_own = c_hi - c_lo;
         if (n_own < 0) n_own = 0;
         if (!exact) {
-            irregular = !lo_found || !closed || __any_sync(FULL, dup_any != 0u);
-            if (irregular) { finish(); return; }   // the tile is analysed again by the exact evaluation
+            // not covered here: a range that does not begin / end at a chunk closer, or one that hands a backlog on
+            irregular = !lo_found || !closed || xb != 0;
+            if (irregular) {                       // the tile is analysed again by the exact evaluation
+                if (lane == 0) {                   // (statistics: why)
+                    if (!lo_found) atomicAdd(&p.result->prof[12], 1ull);
+                    if (!closed) atomicAdd(&p.result->prof[13], 1ull);
+                    if (xb != 0) atomicAdd(&p.result->prof[14], 1ull);
+                }
+                finish(); return;
+            }
         }
         __syncwarp();
         auto T_at = [&](int js, int w) -> uint32_t & { return tempS[(js * 32 + lane) * TWD + w]; };
@@ -572,16 +623,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 const uint32_t ACT = act_mask(js, n, c0);
                 const uint32_t Fr = T_at(js, I_F);
                 const uint32_t S = T_at(js, I_S) & ACT, Lm = L_of(Fr, pk) & ACT, Mm = T_at(js, I_H) & ACT, FmA = Fr & ACT;
-                uint32_t HOT = 0;
-                int xin = 0, out = 0;
-                if (Mm) out = eval_backlog(0, Mm, FmA, S, Lm, HOT);
-                for (;;) {
-                    int nx = __shfl_up_sync(FULL, out, 1);
-                    if (lane == 0) nx = x;
-                    const bool ch = nx != xin;
-                    if (!__any_sync(FULL, ch)) break;
-                    if (ch) { xin = nx; if (xin != 0 || Mm) out = eval_backlog(xin, Mm, FmA, S, Lm, HOT); else { out = 0; HOT = 0; } }
-                }
+                int out;
+                const uint32_t HOT = exact_step(x, Mm, FmA, S, Lm, out);
                 x = __shfl_sync(FULL, out, 31);
                 if (js == RS - 1) v_nom = __shfl_sync(FULL, out, 32 - HLANES - 1);
                 T_at(js, I_H) = HOT;
