@@ -41,13 +41,13 @@ constexpr int RANGE = V5_RANGE;
 constexpr int MARGIN = 12;               // characters starting in the last 12 window bytes lack forward context
 constexpr int LPAD = 16;                 // bytes in front of the window (previous character)
 constexpr int XBYTES = LPAD + WIN + 16;
-constexpr int SPAD = 160;                // slack in front of the first owned character in the split stage
-constexpr int SSTAGE = SPAD + 16 + STEP + 48;
+constexpr int SSTAGE = 5 * 36 * 4;          // pass D: bit stage (up to 5 value planes, 36 words each)
 constexpr int TCAP = 320;                // tokens staged per step; steps with more write their pairs directly
 constexpr int TSTAGE = (TCAP + 2) * 8;
 constexpr int TWG = 12;                  // generic rules: words per lane-word in the (separate) state buffers
 enum { BAR_AGG = 1, BAR_PRE = 3 };
 static_assert(RANGE == WIN - HALO && HALO % 32 == 0 && RANGE % 16 == 0, "geometry");
+static_assert(TSTAGE >= STEP + 64, "the token stage doubles as the byte stage of partly owned split-mask chunks");
 
 struct WAgg { int n_own, ntok, lft, v, flags, pad[3]; };
 struct Slot { unsigned long long G, K, base; int mode, x_in; };
@@ -240,6 +240,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
 #ifdef LATOK_PROFILE
     long long _prof_t = clock64();
 #endif
+    for (int i = lane; i < 5 * 36; i += 32) reinterpret_cast<uint32_t *>(sst)[i] = 0;     // bit stage of pass D
+    __syncwarp();
 
     // ---- window load: TMA bulk copy of the 16-byte aligned interior, plain loads for the ragged end
     auto begin_load = [&](long long r, int b) -> bool {
@@ -772,7 +774,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         // range-relative character index of the first character of the string that is open at c_lo (may be negative)
         int cur_base = c_lo - (int)(long long)(G_in - base_in);
         int ktok = 0;                      // tokens of the range before this step
-        uint32_t prev_tailw = 0;
         const bool spans_direct_all = direct_spans || !closed || !lo_found;
 #pragma unroll 1
         for (int js = 0; js < RS; ++js) {
@@ -800,89 +801,88 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
 #pragma unroll
             for (int q = 0; q < NV; ++q) SPLIT |= V[q];
             // ------------------------------------------------------------ split mask bytes
+            // The value planes are compacted at the bit level: every lane ORs its characters into a per-step bit stream
+            // in shared memory whose origin is the 16-byte boundary at or below the step's first character in the output,
+            // then lane t expands stream bits [32t, 32t+32) into 32 bytes and stores them as two aligned 16-byte chunks.
             if (want_splits && nb > 0) {
-                const unsigned long long Gf = G_in + (unsigned long long)(cf - c_lo);
-                const int a = (int)(Gf & 15ull);
+                const long long Gs0 = (long long)G_in + (cstep0 - c_lo);           // output index of the step's first character
+                const int a = (int)(Gs0 & 15);
+                int8_t *obase = p.splits + (Gs0 - a);                               // 16-byte aligned
+                uint32_t *bp = reinterpret_cast<uint32_t *>(sst);                   // [NV][36] words, kept zero between steps
+                {
+                    const int bpos = a + (c0 - cstep0);
+                    const int w = bpos >> 5, sh = bpos & 31;
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) {
+                        const uint32_t v = V[q] & OWN;                               // nothing but owned characters enters the stream
+                        if (v) {
+                            atomicOr(&bp[q * 36 + w], v << sh);
+                            const uint32_t hi = __funnelshift_l(v, 0u, sh);          // bits that spill into the next word
+                            if (hi) atomicOr(&bp[q * 36 + w + 1], hi);
+                        }
+                    }
+                }
+                __syncwarp();
+                const int bf = a + (cf - cstep0), be = bf + nb;                     // owned stream positions [bf, be)
+                uint32_t Vs[NV];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) { Vs[q] = bp[q * 36 + lane]; bp[q * 36 + lane] = 0; }
                 uint32_t W[8];
-                if (kDefault) {
-                    const uint32_t qlo = (V[0] & 0x0F0F0F0Fu) | ((V[1] & 0x0F0F0F0Fu) << 4);
-                    const uint32_t qhi = ((V[0] >> 4) & 0x0F0F0F0Fu) | (V[1] & 0xF0F0F0F0u);
+                auto expand = [&](const uint32_t *Vx) {
+                    if (kDefault) {
+                        const uint32_t qlo = (Vx[0] & 0x0F0F0F0Fu) | ((Vx[1] & 0x0F0F0F0Fu) << 4);
+                        const uint32_t qhi = ((Vx[0] >> 4) & 0x0F0F0F0Fu) | (Vx[1] & 0xF0F0F0F0u);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        W[2 * g] = lutv[(qlo >> (8 * g)) & 0xFFu];
-                        W[2 * g + 1] = lutv[(qhi >> (8 * g)) & 0xFFu];
+                        for (int g = 0; g < 4; ++g) {
+                            W[2 * g] = lutv[(qlo >> (8 * g)) & 0xFFu];
+                            W[2 * g + 1] = lutv[(qhi >> (8 * g)) & 0xFFu];
+                        }
+                        if (Vx[2]) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) W[g] += spread4((Vx[2] >> (4 * g)) & 15u) << 2;
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            uint32_t w = 0;
+#pragma unroll
+                            for (int q = 0; q < NV; ++q) w += spread4((Vx[q] >> (4 * g)) & 15u) << q;
+                            W[g] = w;
+                        }
                     }
-                    if (V[2]) {
+                };
+                expand(Vs);
+                const int p0 = 32 * lane;
+                const uint4 c1 = make_uint4(W[0], W[1], W[2], W[3]), c2 = make_uint4(W[4], W[5], W[6], W[7]);
+                if (p0 >= bf && p0 + 16 <= be) *reinterpret_cast<uint4 *>(obase + p0) = c1;
+                if (p0 + 16 >= bf && p0 + 32 <= be) *reinterpret_cast<uint4 *>(obase + p0 + 16) = c2;
+                // the (at most two) chunks that are only partly owned go through a byte stage
+                uint8_t *bst = reinterpret_cast<uint8_t *>(tst);                    // (the token stage is idle here)
+                *reinterpret_cast<uint4 *>(bst + p0) = c1;
+                *reinterpret_cast<uint4 *>(bst + p0 + 16) = c2;
+                if (be > 1024) {          // stream positions 1024.. (the step holds up to 1025 characters, plus the alignment)
+                    uint32_t Vt[NV];
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) W[g] += spread4((V[2] >> (4 * g)) & 15u) << 2;
-                    }
-                } else {
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        uint32_t w = 0;
-#pragma unroll
-                        for (int q = 0; q < NV; ++q) w += spread4((V[q] >> (4 * g)) & 15u) << q;
-                        W[g] = w;
-                    }
-                }
-                uint32_t tailw = 0;       // the last 4 characters of this lane, for the next lane's first word
-                if (n >= 4) {
-                    const int sft = n - 4;
-#pragma unroll
-                    for (int q = 0; q < NV; ++q) tailw += spread4((V[q] >> sft) & 15u) << q;
-                }
-                uint32_t headw = __shfl_up_sync(FULL, tailw, 1);
-                if (lane == 0) headw = prev_tailw;
-                const bool slow = __any_sync(FULL, wrel >= 32 && n < 4);       // malformed UTF-8 only
-                const int o = SPAD + a + (c0 - cf);                 // staging offset of this lane's first character
-                const bool act = o >= 4 && n > 0;
-                if (!slow) {
-                    // words are written by the lane that owns their LAST byte: no partial words, no races
-                    const int s = o & 3;
-                    const int cnt = (s + n) >> 2;
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(sst) + (o >> 2);
-                    const int sh = 32 - 8 * s;
-                    uint32_t prev = headw;
-                    uint32_t Wo[9];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { Wo[i] = s ? __funnelshift_r(prev, W[i], sh) : W[i]; prev = W[i]; }
-                    Wo[8] = __funnelshift_r(prev, 0u, sh);
-                    // first the word that holds this lane's trailing bytes (its upper bytes belong to the next lane, which
-                    // overwrites the whole word below), then, after the warp has re-converged, the full words
-                    if (act && ((s + n) & 3) != 0) {
-                        uint32_t tw = Wo[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) if (i == cnt) tw = Wo[i];
-                        dst[cnt] = tw;
-                    }
+                    for (int q = 0; q < NV; ++q) Vt[q] = bp[q * 36 + 32];
                     __syncwarp();
-                    if (act) {
+                    if (lane == 0) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) if (i < cnt) dst[i] = Wo[i];
-                        if (8 < cnt) dst[8] = Wo[8];
+                        for (int q = 0; q < NV; ++q) { bp[q * 36 + 32] = 0; bp[q * 36 + 33] = 0; }
                     }
-                } else if (act) {
-                    for (int jj = 0; jj < n; ++jj) {
-                        uint32_t vv = 0;
-#pragma unroll
-                        for (int q = 0; q < NV; ++q) vv |= ((V[q] >> jj) & 1u) << q;
-                        sst[o + jj] = (uint8_t)vv;
+                    expand(Vt);
+                    if (lane == 0) {
+                        *reinterpret_cast<uint4 *>(bst + 1024) = make_uint4(W[0], W[1], W[2], W[3]);
+                        *reinterpret_cast<uint4 *>(bst + 1040) = make_uint4(W[4], W[5], W[6], W[7]);
                     }
                 }
-                prev_tailw = __shfl_sync(FULL, tailw, 31);
                 __syncwarp();
-                int8_t *dst = p.splits + Gf;
-                const uint8_t *srcb = sst + SPAD + a;
-                const int hb = min((16 - a) & 15, nb);
-                if (lane < hb) dst[lane] = (int8_t)srcb[lane];
-                const int nch = (nb - hb) >> 4;
-                for (int i = lane; i < nch; i += 32)
-                    *reinterpret_cast<uint4 *>(dst + hb + 16 * i) = *reinterpret_cast<const uint4 *>(srcb + hb + 16 * i);
-                const int done = hb + (nch << 4);
-                if (lane < nb - done) dst[done + lane] = (int8_t)srcb[done + lane];
+                {
+                    const int hend = min((bf + 15) & ~15, be);                       // head: [bf, hend)
+                    if (lane < hend - bf) obase[bf + lane] = (int8_t)bst[bf + lane];
+                    const int tbeg = max(be & ~15, hend);                            // tail: [tbeg, be)
+                    if (lane < be - tbeg) obase[tbeg + lane] = (int8_t)bst[tbeg + lane];
+                }
                 __syncwarp();
-            } else if (want_splits) {
-                prev_tailw = 0;
             }
             // ------------------------------------------------------------ token spans
             // latest owned string start in the lanes before this one (else: the one open when the step began)
