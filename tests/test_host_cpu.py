@@ -172,3 +172,20 @@ def test_two_rank_count_exchange_over_gloo():
     assert co0[:-1] + co1 == whole.char_offsets.tolist()
     assert to0[:-1] + to1 == whole.tok_offsets.tolist()
     assert sp0 + sp1 == whole.spans.tolist()
+
+
+def test_bit_plane_primitives_selftest(tmp_path):
+    """latok_bits.h (byte->plane transpose, bit-sliced ASCII classifier, squeeze, carry-add block mask, flood) is
+    host-compilable: tools/bits_selftest.cpp checks it against the generated class table and scalar loops."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "bits_selftest"
+    subprocess.run([gxx, "-O1", "-std=c++17", "-w", "-I", str(root / "latok_b200" / "csrc"),
+                    str(root / "tools" / "bits_selftest.cpp"), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "bits selftest ok" in out.stdout
