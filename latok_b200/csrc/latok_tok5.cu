@@ -56,8 +56,8 @@ struct Ctl {
     int tile_id[2], tk_cnt[2], tk_flag[2], pad0[2];
     Slot slot[2];
     WAgg wagg[2][NW];
-    int xch[NW + 1];
-    unsigned xgen[NW + 1];
+    int xfu[NW], xfv[NW];                // exact evaluation: backlog transfer function of every range of the tile
+    unsigned xfgen[NW];
     RInfo rinfo[NW][2];
     int tokstep[NW][2][RS];              // tokens per step
     int nsa[NW][2][RS];                  // first split after the step (range-relative character index, -1: none)
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         for (int i = threadIdx.x; i < n16; i += NTH) reinterpret_cast<uint4 *>(tableS)[i] = __ldg(src + i);
         if (threadIdx.x == 0) {
             for (int w = 0; w < 2 * NW; ++w) mbar_init(mbar + w, 1);
-            for (int w = 0; w <= NW; ++w) { ctl.xch[w] = 0; ctl.xgen[w] = 0; }
+            for (int w = 0; w < NW; ++w) { ctl.xfu[w] = 0; ctl.xfv[w] = 0; ctl.xfgen[w] = 0; }
             for (int b = 0; b < 2; ++b) { ctl.tile_id[b] = 0; ctl.tk_cnt[b] = 0; ctl.tk_flag[b] = 0; }
         }
     }
@@ -168,9 +168,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 ++round;
                 if (lane == 0) {
                     ctl.slot[s].mode = 1; ctl.slot[s].x_in = x_in;
-                    st_vs32(&ctl.xch[0], x_in);
-                    __threadfence_block();
-                    st_vs32(reinterpret_cast<int *>(&ctl.xgen[0]), (int)round);
                     __threadfence_block();
                 }
                 __syncwarp();
@@ -289,7 +286,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
     // transfer function x -> max(x + u, v) (string start = reset, mark = +1, space = one off but not below 0, end of
     // string = reset), a warp scan composes them, then each lane walks its own events once with the backlog that
     // really enters it.  Returns the hot closers; `x` is the backlog entering the step, `out` leaves this lane-word.
-    auto exact_step = [&](int x, uint32_t Mm, uint32_t FmA, uint32_t S, uint32_t Lm, int &out) -> uint32_t {
+    auto lane_fn_scan = [&](uint32_t Mm, uint32_t FmA, uint32_t S, uint32_t Lm) -> Fn {      // inclusive scan over the lanes
         Fn f = fn_id();
         {
             uint32_t evs = Mm | FmA | S | Lm;
@@ -307,6 +304,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             const int ou = __shfl_up_sync(FULL, inc.u, d), ov = __shfl_up_sync(FULL, inc.v, d);
             if (lane >= d) inc = fn_compose(Fn{ou, ov}, inc);
         }
+        return inc;
+    };
+    auto exact_step = [&](int x, uint32_t Mm, uint32_t FmA, uint32_t S, uint32_t Lm, int &out) -> uint32_t {
+        const Fn inc = lane_fn_scan(Mm, FmA, S, Lm);
         const int eu = __shfl_up_sync(FULL, inc.u, 1), ev2 = __shfl_up_sync(FULL, inc.v, 1);
         const int xin = lane ? fn_apply(Fn{eu, ev2}, x) : x;
         uint32_t HOT = 0;
@@ -314,12 +315,33 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         if (xin != 0 || Mm) out = eval_backlog(xin, Mm, FmA, S, Lm, HOT);
         return HOT;
     };
+    // exact evaluation: publish this range's transfer function / collect the backlog that enters it from the tile's
+    // backlog-in and the functions of the ranges before it (all warps compute theirs at the same time)
+    auto publish_fn = [&](Fn f, unsigned round) {
+        if (lane == 0) {
+            st_vs32(&ctl.xfu[cw], f.u); st_vs32(&ctl.xfv[cw], f.v);
+            __threadfence_block();
+            st_vs32(reinterpret_cast<int *>(&ctl.xfgen[cw]), (int)round);
+        }
+    };
+    auto backlog_in = [&](int x_tile, unsigned round) -> int {
+        int fu = 0, fv = NEG;
+        if (lane < cw) {
+            unsigned spins = 0;
+            while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xfgen[lane])) != round) { if (++spins > (1u << 26)) { atomicOr(&p.result->error, 1u); break; } }
+            fu = ld_vs32(&ctl.xfu[lane]); fv = ld_vs32(&ctl.xfv[lane]);
+        }
+        __syncwarp();
+        int x = x_tile;
+        for (int i = 0; i < cw; ++i) x = fn_apply(Fn{__shfl_sync(FULL, fu, i), __shfl_sync(FULL, fv, i)}, x);
+        return x;
+    };
 
     // results of the analysis that are posted right away (the rest goes to ctl.rinfo for pass D)
     int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0; bool a_irregular = false;
 
     // ================================================================================================= analysis
-    auto analyze = [&](const long long r, const int buf, const bool exact, const unsigned round) {
+    auto analyze = [&](const long long r, const int buf, const bool exact, const unsigned round, const int x_tile) {
         const long long w0 = r * (long long)RANGE;
         const bool have = r < p.nranges, last_range = r == p.nranges - 1;
         uint8_t *X = Xof(buf);
@@ -337,16 +359,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         };
         if (!have) {
             if (exact) {      // pass the backlog on
-                int x = 0;
-                if (lane == 0) {
-                    unsigned spins = 0;
-                    while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xgen[cw])) != round) { if (++spins > (1u << 26)) break; }
-                    x = ld_vs32(&ctl.xch[cw]);
-                    st_vs32(&ctl.xch[cw + 1], x);
-                    __threadfence_block();
-                    st_vs32(reinterpret_cast<int *>(&ctl.xgen[cw + 1]), (int)round);
-                }
-                v_out = __shfl_sync(FULL, x, 0);
+                publish_fn(fn_id(), round);
+                v_out = backlog_in(x_tile, round);
             }
             c_hi = 0;
             finish();
@@ -610,13 +624,23 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         };
         // ---------------------------------------------------------------- pass B (exact only): backlog mark by mark
         if (exact) {
-            int x = 0;
-            if (lane == 0) {
-                unsigned spins = 0;
-                while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xgen[cw])) != round) { if (++spins > (1u << 26)) break; }
-                x = ld_vs32(&ctl.xch[cw]);
+            // B1: the range as one transfer function (up to the last owned character), for the ranges after this one
+            {
+                Fn rf = fn_id();
+#pragma unroll 1
+                for (int js = 0; js < RS; ++js) {
+                    const uint32_t pk = T_at(js, I_K);
+                    const int n = pk_n(pk), c0 = pk_c0(pk);
+                    const uint32_t ACT = act_mask(js, n, c0);
+                    const uint32_t Fr = T_at(js, I_F);
+                    const Fn inc = lane_fn_scan(T_at(js, I_H) & ACT, Fr & ACT, T_at(js, I_S) & ACT, L_of(Fr, pk) & ACT);
+                    const int src = (js == RS - 1 && !closed) ? 32 - HLANES - 1 : 31;
+                    rf = fn_compose(rf, Fn{__shfl_sync(FULL, inc.u, src), __shfl_sync(FULL, inc.v, src)});
+                }
+                publish_fn(rf, round);
             }
-            x = __shfl_sync(FULL, x, 0);
+            // B2: the backlog that really enters, then mark by mark
+            int x = backlog_in(x_tile, round);
             int v_nom = 0;
 #pragma unroll 1
             for (int js = 0; js < RS; ++js) {
@@ -632,11 +656,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 T_at(js, I_H) = HOT;
             }
             v_out = closed ? x : v_nom;
-            if (lane == 0) {
-                st_vs32(&ctl.xch[cw + 1], v_out);
-                __threadfence_block();
-                st_vs32(reinterpret_cast<int *>(&ctl.xgen[cw + 1]), (int)round);
-            }
             // the chunk still open at the end of the trusted halo: hot if a backlog is pending, else look ahead for a mark
             if (!closed) {
                 const uint32_t pk = T_at(RS - 1, I_K);
@@ -1067,7 +1086,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             if (ctl.slot[s].mode == 0) break;
             ++round;
             if (r < p.nranges) plain_load(r, s);
-            analyze(r, s, true, round);
+            analyze(r, s, true, round, ctl.slot[s].x_in);
             exact_done = true;
             post(s);
         }
@@ -1105,7 +1124,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
             if (s == 0 ? pending[0] : pending[1]) wait_window(s, phase_bits);
             __syncwarp();
             PROF5(0);
-            analyze((long long)tile_cur * NW + cw, s, false, 0u);
+            analyze((long long)tile_cur * NW + cw, s, false, 0u, 0);
             post(s);
         } else {
             nb_arrive(BAR_AGG + s, NTH);                 // tells the service warp that the tickets have run out
