@@ -793,7 +793,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
         // range-relative character index of the first character of the string that is open at c_lo (may be negative)
         int cur_base = c_lo - (int)(long long)(G_in - base_in);
         int ktok = 0;                      // tokens of the range before this step
-        const bool spans_direct_all = direct_spans || !closed || !lo_found;
+        const bool spans_direct_all = direct_spans || !closed || !lo_found ||
+                                      K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens;   // (the direct path checks every pair)
 #pragma unroll 1
         for (int js = 0; js < RS; ++js) {
             const uint32_t *t = tempS + (js * 32 + lane) * TWD;
@@ -934,21 +935,22 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 if (!direct && !multi_f) {
                     // bit-reversed planes: __clz walks the tokens in ascending order, the first split after a token is the
                     // highest bit below it.  At most one string start per lane-word here.
+                    // (positions are handled as q = 31 - position, the index FLO returns on the reversed planes)
                     uint32_t evr = __brev(E);
                     const uint32_t spr = __brev(SPq), e2r = __brev(E & ~SPLIT);     // e2r: the span began one character earlier
-                    const int fpos = FO ? 31 - __clz(FO) : 64;
-                    const int offA = c0 - lf_excl;                                   // index = position in the lane-word + off
-                    const int nse = nextsplit >= 0 ? nextsplit - c0 : -(1 << 28);
+                    const int fq = FO ? (int)__clz(FO) : -64;                        // q of the string start inside this lane-word
+                    const int offA = c0 - lf_excl + 31, offB = fq;                   // string-relative index = off - q
+                    const int nse = nextsplit >= 0 ? 31 - (nextsplit - c0) : (1 << 28);
                     int2 *dp = tst + ka + tp;
                     while (evr) {
-                        const int i = __clz(evr);
-                        const uint32_t bit = 0x80000000u >> i;
+                        const int q = 31 - __clz(evr);                              // FLO
+                        const uint32_t bit = 1u << q;
                         evr ^= bit;
-                        const int off = i >= fpos ? -fpos : offA;
-                        const int e = __clz(spr & (bit - 1u));
-                        const int sidx = i + off - ((e2r & bit) ? 1 : 0);
-                        const int eidx = (e < 32 ? e : nse) + off;
-                        *dp++ = make_int2(sidx, eidx);
+                        const int off = q <= fq ? offB : offA;
+                        const uint32_t ab = spr & (bit - 1u);
+                        const int qe = ab ? 31 - __clz(ab) : nse;                    // FLO; the first split after the token
+                        const int sidx = off - q - ((e2r & bit) ? 1 : 0);
+                        *dp++ = make_int2(sidx, off - qe);
                     }
                 } else {
                 uint32_t ev = E;
@@ -989,17 +991,16 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                     }
                 }
                 if (!direct) {
+                    // stage slot j <-> pair (Ks - ka) + j of the output, so 16-byte chunks line up; the first and last chunk
+                    // may hold one pair only
                     __syncwarp();
-                    int2 *dst = reinterpret_cast<int2 *>(p.spans) + Ks;
-                    long long room = p.cap_tokens - (long long)Ks;
-                    const int nt = room <= 0 ? 0 : (room < ntok_step ? (int)room : ntok_step);
-                    const int hb = min(ka, nt);                       // pairs in front of the first 16-byte boundary
-                    if (lane < hb) dst[lane] = tst[ka + lane];
-                    const int nch = (nt - hb) >> 1;
-                    for (int i = lane; i < nch; i += 32)
-                        *reinterpret_cast<uint4 *>(dst + hb + 2 * i) = *reinterpret_cast<const uint4 *>(tst + ka + hb + 2 * i);
-                    const int done = hb + 2 * nch;
-                    if (lane < nt - done) dst[done + lane] = tst[ka + done + lane];
+                    int2 *gb = reinterpret_cast<int2 *>(p.spans) + (Ks - (unsigned long long)ka);
+                    const int tot = ka + ntok_step;
+                    for (int j = 2 * lane; j < tot; j += 64) {
+                        if (j >= ka && j + 1 < tot) *reinterpret_cast<uint4 *>(gb + j) = *reinterpret_cast<const uint4 *>(tst + j);
+                        else if (j >= ka) gb[j] = tst[j];
+                        else if (j + 1 < tot) gb[j + 1] = tst[j + 1];
+                    }
                     __syncwarp();
                 }
             }
