@@ -126,9 +126,9 @@ LATOK_HD uint32_t bits_low(int k) { return k <= 0 ? 0u : (k >= 32 ? 0xFFFFFFFFu 
 template <int NP>
 LATOK_HD void squeeze_planes(uint32_t P[NP], uint32_t &F, uint32_t lead, uint32_t vmask)
 {
+    // (the planes hold nothing at continuation bytes: the ASCII classifier leaves bytes >= 0x80 empty and multi-byte
+    // characters are patched in at their lead byte; only the string-start map can point at one, in malformed input)
     uint32_t del = lead ? (~lead & vmask) : 0u;
-#pragma unroll
-    for (int f = 0; f < NP; ++f) P[f] &= lead;
     F &= lead;
     while (del) {
         const int top = 31 - (int)bits_clz(del);

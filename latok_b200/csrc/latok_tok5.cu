@@ -428,8 +428,9 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                     const int k = __ffs(mm) - 1; mm &= mm - 1;
                     const uint32_t e = mb_entry(src + k, tb, p.tl.high_class);
                     const uint32_t fw = e < 256u ? (e < 128u ? tb.ascii_feat[e] : 0u) : tb.class_feat[e - 256u];
+                    const uint32_t bitk = 1u << k;
 #pragma unroll
-                    for (int f = 0; f < NBASE; ++f) Pc[f] |= ((fw >> f) & 1u) << k;
+                    for (int f = 0; f < NBASE; ++f) if (fw & (1u << f)) Pc[f] |= bitk;
                 }
                 Fc = sb;
                 squeeze_planes<NBASE>(Pc, Fc, leadc, valid);
@@ -807,7 +808,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const 
                 for (int q = 0; q < NV; ++q) V[q] = t[q];
                 E = t[I_E]; Sraw = t[I_S]; Fm = t[I_F]; pk = t[I_K];
             }
-            const uint32_t lead = leadS[js * 32 + lane];
             const int n = pk_n(pk), c0 = pk_c0(pk), tp = pk_tp(pk);
             const int wrel = nb_win - (js * STEP + lane * 32);          // data bytes from this lane-word on
             const bool has_term = (unsigned)wrel < 32u;
