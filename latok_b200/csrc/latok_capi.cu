@@ -119,26 +119,28 @@ bool same_rows(const uint32_t *a, int na, const uint32_t *b, int nb)
 struct latok_b200_engine {
     int device = 0;
     int n_sm = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, aux = nullptr;   // aux: string index of the next batch while the previous one is tokenized
+    cudaEvent_t ev_in = nullptr, ev_index[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    int slot = 0;                                   // which of the two index / result sets the current batch uses
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     TableLayout tl{};
     RuleSet rules{};
     DevBuf<uint8_t> d_table, d_in, d_scratch, d_scratch2, d_scratch3;
-    DevBuf<long long> d_off, d_first, d_char_off, d_tok_off;
+    DevBuf<long long> d_off, d_first[2], d_char_off, d_tok_off;
     DevBuf<int8_t> d_splits, d_feats, d_matrix;
     DevBuf<int32_t> d_spans;
     DevBuf<AggRec> agg;
     DevBuf<IncRec> inc;
     DevBuf<OpenSums> osum;
     DevBuf<unsigned long long> span_scratch;
-    DevBuf<Result> d_result;
+    DevBuf<Result> d_result[2];
     PinBuf<uint8_t> h_in;
     PinBuf<long long> h_off;
-    PinBuf<Result> h_result;
+    PinBuf<Result> h_result[2];
     unsigned epoch = 0;
     long long launches = 0;
     // current batch
-    bool submitted = false, sized = false;
+    bool submitted = false, sized = false, inputs_on_stream = false;
     const uint8_t *cur_in = nullptr;
     const long long *cur_off = nullptr;
     long long n_strings = 0, n_bytes = 0;
@@ -237,12 +239,20 @@ int latok_b200_create(int device, size_t max_batch_bytes, int64_t max_strings, l
         CU(cudaSetDevice(device));
         CU(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
         CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
         CU(cudaEventCreate(&e->ev_k0)); CU(cudaEventCreate(&e->ev_k1));
+        CU(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&e->ev_index[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+        }
         CU(cudaEventCreate(&e->ev_t0)); CU(cudaEventCreate(&e->ev_t1));
         if (int r = build_table(e)) return r;
         e->rules = default_rules();
-        if (int r = e->d_result.ensure(1, true)) return r;
-        if (int r = e->h_result.ensure(1)) return r;
+        for (int i = 0; i < 2; ++i) {
+            if (int r = e->d_result[i].ensure(1, true)) return r;
+            if (int r = e->h_result[i].ensure(1)) return r;
+        }
         if (max_batch_bytes) {
             if (int r = e->d_in.ensure(max_batch_bytes + 64)) return r;
             if (int r = e->d_splits.ensure(max_batch_bytes + 64)) return r;
@@ -265,12 +275,16 @@ int latok_b200_destroy(latok_b200_engine *e)
     if (!e) return LATOK_B200_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->aux) cudaStreamSynchronize(e->aux);
     e->d_table.release(); e->d_in.release(); e->d_scratch.release(); e->d_scratch2.release(); e->d_scratch3.release();
-    e->d_off.release(); e->d_first.release(); e->d_char_off.release(); e->d_tok_off.release();
+    e->d_off.release(); e->d_first[0].release(); e->d_first[1].release(); e->d_char_off.release(); e->d_tok_off.release();
     e->d_splits.release(); e->d_feats.release(); e->d_matrix.release(); e->d_spans.release();
     e->agg.release(); e->inc.release(); e->osum.release(); e->span_scratch.release();
-    e->d_result.release();
-    e->h_in.release(); e->h_off.release(); e->h_result.release();
+    e->d_result[0].release(); e->d_result[1].release();
+    e->h_in.release(); e->h_off.release(); e->h_result[0].release(); e->h_result[1].release();
+    if (e->ev_in) cudaEventDestroy(e->ev_in);
+    for (int i = 0; i < 2; ++i) { if (e->ev_index[i]) cudaEventDestroy(e->ev_index[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); }
+    if (e->aux) cudaStreamDestroy(e->aux);
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
     if (e->ev_k1) cudaEventDestroy(e->ev_k1);
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
@@ -315,7 +329,8 @@ static int run_device(latok_b200_engine *e)
     const int unit = use5 ? V5_RANGE : TILE;
     const long long nunits = e->n_bytes / unit + 1;
     const long long ntiles = use5 ? (nunits + V5_NW - 1) / V5_NW : nunits;
-    if (int r = e->d_first.ensure((size_t)nunits + 1)) return r;
+    const int slot = e->slot ^= 1;
+    if (int r = e->d_first[slot].ensure((size_t)nunits + 1)) return r;
     // the status word of every aggregate record carries the launch epoch, so records are zeroed only when (re)allocated
     if ((size_t)ntiles > e->agg.cap) { if (int r = e->agg.ensure((size_t)ntiles, true)) return r; }
     if (int r = e->inc.ensure((size_t)ntiles)) return r;
@@ -335,14 +350,14 @@ static int run_device(latok_b200_engine *e)
     Params p;
     memset(&p, 0, sizeof p);
     p.in = e->cur_in; p.n_bytes = e->n_bytes; p.offsets = e->cur_off; p.n_strings = e->n_strings;
-    p.tile_first_str = e->d_first.p; p.ntiles = ntiles; p.nranges = nunits;
+    p.tile_first_str = e->d_first[slot].p; p.ntiles = ntiles; p.nranges = nunits;
     p.splits = e->d_splits.p; p.char_off = e->d_char_off.p; p.spans = e->d_spans.p; p.tok_off = e->d_tok_off.p;
     p.feats = e->d_feats.p; p.matrix = e->d_matrix.p;
     p.cap_tokens = (long long)(e->d_spans.cap / 2);
     p.what = e->what;
     p.agg = e->agg.p; p.inc = e->inc.p; p.osum = e->osum.p; p.span_scratch = e->span_scratch.p; p.epoch = e->epoch;
-    p.ticket = &e->d_result.p->ticket; p.ticket_base = 0;
-    p.result = e->d_result.p;
+    p.ticket = &e->d_result[slot].p->ticket; p.ticket_base = 0;
+    p.result = e->d_result[slot].p;
     p.table_blob = e->d_table.p; p.tl = e->tl; p.rules = e->rules;
     int grid = e->n_sm * (use5 ? tokenize5_ctas_per_sm(e->tl, e->rules.is_default != 0)
                                : tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words));
@@ -350,12 +365,22 @@ static int run_device(latok_b200_engine *e)
     if (!use5) { if (int r = e->span_scratch.ensure((size_t)grid * 2 * SPAN_SCRATCH)) return r; }
     p.span_scratch = e->span_scratch.p;
 
-    CU(cudaMemsetAsync(e->d_result.p, 0, sizeof(Result), e->stream));
-    CU(launch_tile_index(e->cur_off, e->n_strings, e->n_bytes, e->d_first.p, nunits, unit, e->d_result.p, e->stream));
+    // The string index of this batch is built on the aux stream, so that with back-to-back submits it overlaps the
+    // tokenize kernel of the previous batch (two index / result sets alternate).
+    if (e->inputs_on_stream) {                       // host submit: the offsets arrive by a copy on the main stream
+        CU(cudaEventRecord(e->ev_in, e->stream));
+        CU(cudaStreamWaitEvent(e->aux, e->ev_in, 0));
+    }
+    CU(cudaStreamWaitEvent(e->aux, e->ev_done[slot], 0));     // this set's previous batch has been tokenized and read back
+    CU(cudaMemsetAsync(e->d_result[slot].p, 0, sizeof(Result), e->aux));
+    CU(launch_tile_index(e->cur_off, e->n_strings, e->n_bytes, e->d_first[slot].p, nunits, unit, e->d_result[slot].p, e->aux));
+    CU(cudaEventRecord(e->ev_index[slot], e->aux));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_index[slot], 0));
     CU(cudaEventRecord(e->ev_k0, e->stream));
     CU(use5 ? launch_tokenize5(p, grid, e->stream) : launch_tokenize(p, grid, e->stream));
     CU(cudaEventRecord(e->ev_k1, e->stream));
-    CU(cudaMemcpyAsync(e->h_result.p, e->d_result.p, sizeof(Result), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(e->h_result[slot].p, e->d_result[slot].p, sizeof(Result), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaEventRecord(e->ev_done[slot], e->stream));
     e->launches += 2;
     e->submitted = true;
     e->sized = false;
@@ -406,6 +431,7 @@ int latok_b200_submit(latok_b200_engine *e, const uint8_t *utf8, const int64_t *
     CU(cudaMemcpyAsync(e->d_off.p, src_o, sizeof(long long) * ((size_t)n_strings + 1), cudaMemcpyHostToDevice, e->stream));
     e->cur_in = e->d_in.p; e->cur_off = e->d_off.p;
     e->n_strings = n_strings; e->n_bytes = n_bytes; e->what = what;
+    e->inputs_on_stream = true;
     return run_device(e);
 }
 
@@ -421,6 +447,7 @@ int latok_b200_submit_device(latok_b200_engine *e, const uint8_t *d_utf8, const 
     e->submitted = false;
     e->cur_in = d_utf8; e->cur_off = (const long long *)d_offsets;
     e->n_strings = n_strings; e->n_bytes = n_bytes; e->what = what;
+    e->inputs_on_stream = false;
     return run_device(e);
 }
 
@@ -431,7 +458,7 @@ int latok_b200_sizes(latok_b200_engine *e, int64_t *n_chars, int64_t *n_tokens)
     if (int r = set_device(e)) return r;
     for (int attempt = 0; attempt < 4 && !e->sized; ++attempt) {
         CU(cudaStreamSynchronize(e->stream));
-        const Result res = *e->h_result.p;
+        const Result res = *e->h_result[e->slot].p;
         if (res.error & 2u) { e->submitted = false; return fail(LATOK_B200_EINVAL, "offsets must start at 0, be non-decreasing and end at the buffer length"); }
         if (res.error & 1u) { e->submitted = false; return fail(LATOK_B200_EINTERNAL, "device look-back watchdog tripped"); }
         if (res.error & 8u) {

@@ -26,7 +26,13 @@ constexpr int SPAN_SCRATCH = WINB + 64; // per CTA and slot: global stage for ti
 
 // v5 kernel (latok_tok5.cu): one warp analyses a "range" (V5_RS steps of 1 KB, the last V5_HALO bytes shared with the
 // next range), a tile is the V5_NW ranges of one CTA
-constexpr int V5_RS = 4;
+#ifndef LATOK_V5_RS
+#define LATOK_V5_RS 4
+#endif
+#ifndef LATOK_V5_CTAS
+#define LATOK_V5_CTAS 2
+#endif
+constexpr int V5_RS = LATOK_V5_RS;
 constexpr int V5_HALO = 128;
 constexpr int V5_RANGE = V5_RS * 1024 - V5_HALO;
 constexpr int V5_NW = 8;

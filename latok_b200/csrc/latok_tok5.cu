@@ -108,7 +108,7 @@ __device__ __forceinline__ int ld_vs32(const int *p) { int v; asm volatile("ld.v
 __device__ __forceinline__ void st_vs32(int *p, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
 
 template <bool kDefault>
-__global__ void __launch_bounds__(NTH, kDefault ? 2 : 1) tokenize5_kernel(const Params p)
+__global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_kernel(const Params p)
 {
     constexpr int NC = kDefault ? 3 : 4;      // split-count planes
     constexpr int NY = kDefault ? 1 : 4;      // sym-count planes
