@@ -246,3 +246,27 @@ def test_bad_offsets_rejected(engine):
         engine.run_packed(buf, np.array([1, 11], dtype=np.int64))
     # engine still usable afterwards
     check_batch(engine, ["still fine"], label="after error")
+
+
+def test_back_to_back_submits_alternate_index_sets(engine):
+    """Several device-resident batches submitted without waiting in between (the string index of batch i+1 is built on
+    an aux stream while batch i is tokenized; two index / result sets alternate): the results are those of the last one,
+    whichever kernel (v5 for split mask + spans, v4 with token features) each batch used."""
+    torch = pytest.importorskip("torch")
+    from latok_b200.engine import pack_strings
+    batches = [corpus.fuzz_strings(100 + i, 3000 + 700 * i, 60 + 30 * i, "mixed") for i in range(5)]
+    dev = []
+    for texts in batches:
+        b, o = pack_strings(texts)
+        dev.append((torch.from_numpy(b.copy()).cuda(), torch.from_numpy(o.copy()).cuda(), len(texts)))
+    torch.cuda.synchronize()
+    for order, whats in (((0, 1, 2, 3, 4), (3, 3, 3, 3, 3)), ((4, 2, 0, 3, 1), (3, 7, 3, 15, 3)), ((1, 1, 3), (7, 3, 3))):
+        for i, what in zip(order, whats):
+            b, o, n = dev[i]
+            engine.submit_device(b.data_ptr(), o.data_ptr(), n, b.numel(), what)
+        last, what = order[-1], whats[-1]
+        r = engine.fetch()
+        ref = oracle.tokenize_batch(batches[last])
+        assert r.n_chars == ref["n_chars"] and r.n_tokens == ref["n_tokens"]
+        assert np.array_equal(r.splits, ref["splits"]) and np.array_equal(r.spans, ref["spans"])
+        assert np.array_equal(r.char_offsets, ref["char_offsets"]) and np.array_equal(r.tok_offsets, ref["tok_offsets"])
