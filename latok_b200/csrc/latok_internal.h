@@ -35,7 +35,10 @@ constexpr int SPAN_SCRATCH = WINB + 64; // per CTA and slot: global stage for ti
 constexpr int V5_RS = LATOK_V5_RS;
 constexpr int V5_HALO = 128;
 constexpr int V5_RANGE = V5_RS * 1024 - V5_HALO;
-constexpr int V5_NW = 8;
+#ifndef LATOK_V5_NW
+#define LATOK_V5_NW 9
+#endif
+constexpr int V5_NW = LATOK_V5_NW;
 
 constexpr int NFEAT = 25;
 constexpr int MAX_RULE_ROWS = 15;

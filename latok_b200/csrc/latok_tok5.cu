@@ -64,11 +64,12 @@ struct Ctl {
 };
 
 // Per lane-word, between the passes, 8 words live IN PLACE of the lane-word's 32 input bytes (default rules):
-//   after pass A : CNT0 CNT1 CNT2 SYM | S  M/HOT  F  packed        after pass C : V0 V1 V2 E | S  -  F  packed
-// (generic rules: TWG words in a separate buffer: CNT[4] SYM[4] S M/HOT F packed -> V[5] E - - S - F packed);
-// the string-start map of the window (bit = byte) turns into the lane-word's lead-byte mask once it has been read.
+//   after pass A : CNT0 CNT1 CNT2 SYM | S  M/HOT  F  packed        after pass C : V0 V1 V2 E | S  lead  F  packed
+// (generic rules: TWG words in a separate buffer: CNT[4] SYM[4] S M/HOT F packed -> V[5] E - - S lead F packed);
+// the string-start map of the window (bit = byte) turns into the lane-word's lead-byte mask once it has been read and
+// moves into the state in pass C.
 struct Plan {
-    int tables, ctl, mbar, warp0, x[2], sst, tst, sbm[2], temp[2], per_warp, total;
+    int tables, ctl, mbar, warp0, x[2], sst, tst, sbm, temp[2], per_warp, total;
 };
 __host__ __device__ inline Plan plan(const TableLayout &tl, bool is_default)
 {
@@ -81,7 +82,7 @@ __host__ __device__ inline Plan plan(const TableLayout &tl, bool is_default)
     s.x[0] = take(XBYTES); s.x[1] = take(XBYTES);
     s.sst = take(SSTAGE);
     s.tst = take(TSTAGE);
-    s.sbm[0] = take(RS * 32 * 4); s.sbm[1] = take(RS * 32 * 4);
+    s.sbm = take(RS * 32 * 4);
     for (int b = 0; b < 2; ++b) s.temp[b] = is_default ? s.x[b] + LPAD : take(RS * TWG * 32 * 4);
     s.per_warp = o - s.warp0;
     s.total = s.warp0 + NW * s.per_warp;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     uint8_t *sst = wbase + (sp.sst - sp.warp0);
     int2 *tst = reinterpret_cast<int2 *>(wbase + (sp.tst - sp.warp0));
     auto Xof = [&](int b) -> uint8_t * { return wbase + (sp.x[b] - sp.warp0); };
-    auto sbmof = [&](int b) -> uint32_t * { return reinterpret_cast<uint32_t *>(wbase + (sp.sbm[b] - sp.warp0)); };
+    uint32_t *sbmS = reinterpret_cast<uint32_t *>(wbase + (sp.sbm - sp.warp0));
     auto tempof = [&](int b) -> uint32_t * { return reinterpret_cast<uint32_t *>(wbase + (sp.temp[b] - sp.warp0)); };
     Tables tb;
     tb.ascii_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.ascii_feat - p.tl.lutv));
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         const long long w0 = r * (long long)RANGE;
         const bool have = r < p.nranges, last_range = r == p.nranges - 1;
         uint8_t *X = Xof(buf);
-        uint32_t *sbmS = sbmof(buf), *tempS = tempof(buf);
+        uint32_t *tempS = tempof(buf);
         int c_lo = 0, c_hi = CINF, n_own = 0, ntok_range = 0, lft = -1, v_out = 0, far = 0;
         bool closed = true, lo_found = true, irregular = false;
         auto finish = [&]() {
@@ -757,13 +758,14 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 if (FO) lft_max = max(lft_max, c0 + 31 - __clz(FO));
                 // state for pass D, in place
                 const uint32_t pk2 = (pk & 0xC007FFFFu) | ((uint32_t)(ts - mytok) << 19);
+                const uint32_t leadw = sbmS[js * 32 + lane];      // the window's map is rebuilt by the next analysis: keep the mask here
                 if (kDefault) {
                     *reinterpret_cast<uint4 *>(t) = make_uint4(V[0], V[1], V[2], E);
-                    t[I_K] = pk2;
+                    t[I_H] = leadw; t[I_K] = pk2;
                 } else {
 #pragma unroll
                     for (int q = 0; q < NV; ++q) t[q] = V[q];
-                    t[I_E] = E; t[I_K] = pk2;
+                    t[I_E] = E; t[I_H] = leadw; t[I_K] = pk2;
                 }
             }
             lft = __reduce_max_sync(FULL, lft_max);
@@ -781,7 +783,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         const long long w0 = r * (long long)RANGE;
         const long long rem64 = p.n_bytes - w0;
         const int nb_win = rem64 > (long long)(WIN + 64) ? WIN + 64 : (int)rem64;
-        const uint32_t *tempS = tempof(buf), *leadS = sbmof(buf);
+        const uint32_t *tempS = tempof(buf);
         if (K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens && lane == 0) atomicOr(&p.result->error, 4u);
         if (G_in + (unsigned long long)n_own > (unsigned long long)p.n_bytes || K_in + (unsigned long long)ntok_range > (unsigned long long)p.n_bytes + 1ull) {
             if (lane == 0 && atomicOr(&p.result->error, 8u) == 0u) {
@@ -1018,7 +1020,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     const int wb = int(o - w0);
                     const int js = wb >> 10, tl = (wb >> 5) & 31;
                     const uint32_t *t = tempS + (js * 32 + tl) * TWD;
-                    const uint32_t l_pk = t[I_K], l_E = t[I_E], l_lead = leadS[js * 32 + tl];
+                    const uint32_t l_pk = t[I_K], l_E = t[I_E], l_lead = t[I_H];
                     const int l_c0 = pk_c0(l_pk);
                     const int c = l_c0 + __popc(l_lead & mask_lt_nn(wb & 31));
                     const bool mine = last_range ? (c >= c_lo) : (c >= c_lo && c < c_hi);

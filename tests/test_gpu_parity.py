@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 ALL = 1 | 2 | 4 | 8
 # bytes owned per unit of work (latok_internal.h): a v5 range (one warp), a v4 tile (token-feature / matrix modes) and a
 # v5 tile (8 ranges, one look-back record); tests place interesting things around multiples of each
-UNITS = (3968, 7936, 31744)
+UNITS = (3968, 7936, 9 * 3968)
 TILE = 7936
 
 
@@ -165,7 +165,7 @@ def test_long_space_free_runs_and_walk(engine):
     characters in earlier tiles (latok.c:218-244 has unbounded reach)."""
     cases = []
     for TILE, run in ((7936, 300), (7936, 1000), (7936, 7936 - 50), (7936, 7936 + 300), (7936, 2 * 7936 + 77), (7936, 40000),
-                      (3968, 100), (3968, 130), (3968, 3968 + 300), (31744, 200), (31744, 31744 + 5000), (3968, 70000)):
+                      (3968, 100), (3968, 130), (3968, 3968 + 300), (35712, 200), (35712, 35712 + 5000), (31744, 200), (3968, 70000)):
         base = "x y " * ((TILE - 120) // 4)
         cases.append(base + " " + ",".join(["ab"] * (run // 3)) + " end")                    # no mark: commas split
         cases.append(base + " " + ",".join(["ab"] * (run // 3)) + ",q@r end")                # mark at the very end
