@@ -6,7 +6,7 @@
 //            bytes up to and including the first closer found in the 116 bytes after byte 3968.  Neighbouring
 //            ranges look at the same bytes and agree, so (almost) no block-mask state crosses a range boundary.
 //   step   = 1 KB of a range: lane l holds bytes [32l, 32l+32) as bit-planes (32 characters per register).
-//   tile   = the 8 consecutive ranges of one CTA; one decoupled look-back record per tile (service warp).
+//   tile   = the V5_NW (9) consecutive ranges of one CTA; one decoupled look-back record per tile (service warp).
 //
 // Per range (compute warp, no CTA-wide barrier anywhere on this path):
 //   pass A  forward over the steps, software-pipelined (base planes of step j+1, then context + rules of step j):
@@ -17,7 +17,7 @@
 //           mark-by-mark evaluation, pass B)
 //   pass C  backward over the steps: blank the chunks whose closer is hot, split values
 //           (default_tokenizer.py:121-132), token flags (default_tokenizer.py:148-158), counts
-//   -> the service warp sums the 8 ranges, publishes the tile aggregate, looks back, hands the prefix down
+//   -> the service warp sums the ranges of the tile, publishes the aggregate, looks back, hands the prefix down
 //   pass D  forward: split bytes and (start,end) pairs staged per step in shared memory and written with
 //           aligned 16-byte stores; CSR offsets by one lane per string.
 // The warps run one tile ahead of the look-back: analysis of tile k+1, then pass D of tile k, whose state waits in
