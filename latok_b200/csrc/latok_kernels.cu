@@ -662,25 +662,22 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
             if (lane == 0) { scratch[144 + warp] = cm; scratch[152 + warp] = cs; }
         }
 
-        auto is_split = [&](int c) -> bool {   // c = tile character index; thread-local planes live in splitS
-            int t = c >> 5;
-            while (t + 1 < NT && cprefS[t + 1] <= c) ++t;
-            return (splitS[t] >> (c - cprefS[t])) & 1u;
-        };
-        // feature sums of characters c, c-1, ... down to the token's first character (a split) or c_lo
-        auto walk_back = [&](int c, unsigned acc[7], bool &hit) {
+        // feature sums of characters c, c-1, ... down to the token's first character (a split) or c_lo; `t` = a thread
+        // whose word holds c or a later character (the owner is found by stepping down, the walk is sequential)
+        auto walk_back = [&](int c, int t, unsigned acc[7], bool &hit) {
             hit = false;
             for (; c >= c_lo; --c) {
+                while (t > 0 && cprefS[t] > c) --t;
                 const uint32_t w = wordS[widx(c)] & FEATMASK;
 #pragma unroll
                 for (int g = 0; g < 7; ++g) acc[g] = __vadd4(acc[g], spread4((w >> (4 * g)) & 15u));
-                if (is_split(c)) { hit = true; break; }
+                if ((splitS[t] >> (c - cprefS[t])) & 1u) { hit = true; break; }
             }
         };
         // feature sums of the token still open at the end of the owned range (one thread; token-feature mode)
         auto publish_open_sums = [&]() {
             unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit = false;
-            if (n_own > 0) walk_back(c_hi - 1, acc, hit);
+            if (n_own > 0) walk_back(c_hi - 1, NT - 1, acc, hit);
             uint4 a, b, c4;
             a.x = hit ? 1u : 0u; a.y = a.z = a.w = 0;
             b.x = acc[0]; b.y = acc[1]; b.z = acc[2]; b.w = acc[3];
@@ -955,7 +952,17 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
                 const long long k = (long long)K_in + tp + __popc(E & mask_lt(i)) - 1;
                 if (k < 0 || k >= p.cap_tokens) continue;
                 unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit;
-                walk_back(c0 + i - 1, acc, hit);
+                // the token's characters inside this thread's word: one population count per feature plane
+                {
+                    const int low = max(c_lo - c0, 0);
+                    const uint32_t below = SPLIT & mask_lt(i) & ~mask_lt(low);
+                    hit = below != 0u;
+                    const int sfrom = hit ? 31 - __clz(below) : low;
+                    const uint32_t frag = mask_lt(i) & ~mask_lt(sfrom);
+#pragma unroll
+                    for (int f = 0; f < NFEAT; ++f) acc[f >> 2] += (unsigned)__popc(full[f] & frag) << (8 * (f & 3));   // < 256 each: no carry
+                }
+                if (!hit) walk_back(c0 - 1, tid > 0 ? tid - 1 : 0, acc, hit);   // it began in an earlier thread: character by character
                 for (long long t = tile - 1; !hit && t >= 0; --t) {      // token began in an earlier tile
                     const uint4 *o = reinterpret_cast<const uint4 *>(p.osum + t);
                     const uint4 a = ld_rec(o), b = ld_rec(o + 1), c4 = ld_rec(o + 2);
@@ -964,8 +971,19 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
                     acc[6] = __vadd4(acc[6], c4.z);
                     hit = a.x != 0u;
                 }
+                // the 25-byte row starts at byte 25 k: whole words where they are ours alone, single bytes at the two ends
                 int8_t *row = p.feats + k * NFEAT;
-                for (int f = 0; f < NFEAT; ++f) row[f] = (int8_t)((acc[f >> 2] >> ((f & 3) * 8)) & 0xFFu);
+                const int head = (int)((0u - (unsigned)(k & 3)) & 3u);      // bytes in front of the first 4-byte boundary
+                auto put = [&](int hb) {                                     // hb = head, a compile-time constant per call
+                    for (int q = 0; q < hb; ++q) row[q] = (int8_t)((acc[0] >> (8 * q)) & 0xFFu);
+                    const int nw = (NFEAT - hb) >> 2;
+                    uint32_t *w = reinterpret_cast<uint32_t *>(row + hb);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+                        if (j < nw) w[j] = hb ? __funnelshift_r(acc[j], acc[j + 1], 8 * hb) : acc[j];
+                    for (int q = hb + 4 * nw; q < NFEAT; ++q) row[q] = (int8_t)((acc[q >> 2] >> (8 * (q & 3))) & 0xFFu);
+                };
+                if (head == 0) put(0); else if (head == 1) put(1); else if (head == 2) put(2); else put(3);
             }
         }
 
