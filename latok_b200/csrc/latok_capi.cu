@@ -324,8 +324,8 @@ static int run_device(latok_b200_engine *e)
 {
     // token-feature / matrix modes run the v4 kernel (one CTA per 7 936-byte tile); split mask + spans run v5 (one warp
     // per 3 968-byte range, V5_NW ranges per tile)
-    const bool words = (e->what & (LATOK_B200_FEATS | LATOK_B200_MATRIX)) != 0;
-    const bool use5 = !words && !getenv("LATOK_B200_FORCE_V4");
+    const bool words = (e->what & LATOK_B200_MATRIX) != 0, feats = (e->what & LATOK_B200_FEATS) != 0;
+    const bool use5 = !words && !feats && !getenv("LATOK_B200_FORCE_V4");
     const int unit = use5 ? V5_RANGE : TILE;
     const long long nunits = e->n_bytes / unit + 1;
     const long long ntiles = use5 ? (nunits + V5_NW - 1) / V5_NW : nunits;
@@ -360,7 +360,7 @@ static int run_device(latok_b200_engine *e)
     p.result = e->d_result[slot].p;
     p.table_blob = e->d_table.p; p.tl = e->tl; p.rules = e->rules;
     int grid = e->n_sm * (use5 ? tokenize5_ctas_per_sm(e->tl, e->rules.is_default != 0)
-                               : tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words));
+                               : tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words, feats));
     if ((long long)grid > ntiles) grid = (int)ntiles;
     if (!use5) { if (int r = e->span_scratch.ensure((size_t)grid * 2 * SPAN_SCRATCH)) return r; }
     p.span_scratch = e->span_scratch.p;

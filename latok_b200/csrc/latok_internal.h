@@ -126,8 +126,8 @@ struct Params {
     RuleSet rules;
 };
 
-size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words);
-int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words);
+size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words, bool want_feats);
+int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words, bool want_feats);
 int tokenize5_ctas_per_sm(const TableLayout &tl, bool is_default);
 cudaError_t launch_tokenize5(const Params &p, int grid, cudaStream_t s);
 cudaError_t launch_tile_index(const long long *offsets, long long n_strings, long long n_bytes,

@@ -58,9 +58,9 @@ struct Slot {            // per-tile state handed from the compute warps to the 
 };
 
 struct SmemPlan {
-    int mbar, scal, slots, tile[NBUF], table, spans[2], startbits, leadmask[2], cpref[2], emit[2], tokpref[2], split, edge, scratch, words, total;
+    int mbar, scal, slots, tile[NBUF], table, spans[2], startbits, leadmask[2], cpref[2], emit[2], tokpref[2], split, edge, scratch, words, tails, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(int table_bytes, bool want_words)
+__host__ __device__ inline SmemPlan smem_plan(int table_bytes, bool want_words, bool want_tails = false)
 {
     SmemPlan s; int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
@@ -76,10 +76,11 @@ __host__ __device__ inline SmemPlan smem_plan(int table_bytes, bool want_words)
     s.edge = take(NWARP * 16 * 4);
     s.scratch = take(1024);
     s.words = take(want_words ? (WINB + WINB / 32 + 64) * 4 : 0);
+    s.tails = take(want_tails ? NT * 8 * 4 : 0);      // token-feature mode: per thread, feature sums of its open tail + flag
     s.total = o;
     return s;
 }
-size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words) { return (size_t)smem_plan(tl.total, want_words).total; }
+size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words, bool want_feats) { return (size_t)smem_plan(tl.total, want_words, want_feats).total; }
 
 struct Scalars {          // block-shared scalars
     long long tile_id[NBUF];
@@ -119,11 +120,12 @@ __device__ __forceinline__ void transpose32(uint32_t a[32])
 
 
 
-template <bool kDefault, bool kWords>
+template <bool kDefault, bool kWords, bool kFeats>
 __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(const Params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemPlan sp = smem_plan(p.tl.total, kWords);
+    const SmemPlan sp = smem_plan(p.tl.total, kWords, kFeats);
+    constexpr bool kSync = kWords || kFeats;       // these modes write a tile's outputs with its prefix in hand (not one tile behind)
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + sp.mbar);   // [NBUF]
     Scalars &sc = *reinterpret_cast<Scalars *>(smem + sp.scal);
     Slot *slots = reinterpret_cast<Slot *>(smem + sp.slots);
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
     uint32_t *edgeS = reinterpret_cast<uint32_t *>(smem + sp.edge);
     int *scratch = reinterpret_cast<int *>(smem + sp.scratch);
     uint32_t *wordS = reinterpret_cast<uint32_t *>(smem + sp.words);
+    uint32_t *tailS = reinterpret_cast<uint32_t *>(smem + sp.tails);
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
     if (ld_volatile_u32(&p.result->error) & 2u) return;  // offsets failed validation in tile_index_kernel
@@ -662,22 +665,25 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
             if (lane == 0) { scratch[144 + warp] = cm; scratch[152 + warp] = cs; }
         }
 
-        // feature sums of characters c, c-1, ... down to the token's first character (a split) or c_lo; `t` = a thread
-        // whose word holds c or a later character (the owner is found by stepping down, the walk is sequential)
-        auto walk_back = [&](int c, int t, unsigned acc[7], bool &hit) {
-            hit = false;
-            for (; c >= c_lo; --c) {
-                while (t > 0 && cprefS[t] > c) --t;
-                const uint32_t w = wordS[widx(c)] & FEATMASK;
+        // token-feature mode: 25 population counts of the feature planes over a set of this thread's characters, one byte
+        // per feature (uint8 wrap-around like combine_matrix_rows 1-D, latok.c:342-354)
+        auto plane_sums = [&](uint32_t frag, unsigned acc[7]) {
 #pragma unroll
-                for (int g = 0; g < 7; ++g) acc[g] = __vadd4(acc[g], spread4((w >> (4 * g)) & 15u));
-                if ((splitS[t] >> (c - cprefS[t])) & 1u) { hit = true; break; }
+            for (int f = 0; f < NFEAT; ++f) acc[f >> 2] += (unsigned)__popc(full[f] & frag) << (8 * (f & 3));   // <= 32 each: no carry
+        };
+        // add the open tails of the threads before `t` until one of them holds the token's first character (a split)
+        auto walk_threads = [&](int t, unsigned acc[7], bool &hit) {
+            for (; t >= FIRST_OWNED_THREAD && !hit; --t) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(tailS + t * 8), b = *reinterpret_cast<const uint4 *>(tailS + t * 8 + 4);
+                acc[0] = __vadd4(acc[0], a.x); acc[1] = __vadd4(acc[1], a.y); acc[2] = __vadd4(acc[2], a.z); acc[3] = __vadd4(acc[3], a.w);
+                acc[4] = __vadd4(acc[4], b.x); acc[5] = __vadd4(acc[5], b.y); acc[6] = __vadd4(acc[6], b.z);
+                hit = b.w != 0u;
             }
         };
         // feature sums of the token still open at the end of the owned range (one thread; token-feature mode)
         auto publish_open_sums = [&]() {
             unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0}; bool hit = false;
-            if (n_own > 0) walk_back(c_hi - 1, NT - 1, acc, hit);
+            if (n_own > 0) walk_threads(NT - 1, acc, hit);
             uint4 a, b, c4;
             a.x = hit ? 1u : 0u; a.y = a.z = a.w = 0;
             b.x = acc[0]; b.y = acc[1]; b.z = acc[2]; b.w = acc[3];
@@ -924,7 +930,19 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
                 }
             }
         }
-        if (kWords && want_feats && tid == 0) { publish_open_sums(); __threadfence(); }
+        if (kFeats) {
+            // this thread's open tail: its owned characters from its last split on (all of them if it holds none)
+            const int low = max(c_lo - c0, 0), high = min(n, c_hi - c0);
+            const uint32_t rng = high > low ? (mask_lt(high) & ~mask_lt(low)) : 0u;
+            const uint32_t spl = SPLIT & rng;
+            const uint32_t frag = spl ? (rng & ~mask_lt(31 - __clz(spl))) : rng;
+            unsigned tl[7] = {0, 0, 0, 0, 0, 0, 0};
+            plane_sums(frag, tl);
+            *reinterpret_cast<uint4 *>(tailS + tid * 8) = make_uint4(tl[0], tl[1], tl[2], tl[3]);
+            *reinterpret_cast<uint4 *>(tailS + tid * 8 + 4) = make_uint4(tl[4], tl[5], tl[6], spl ? 1u : 0u);
+            CBAR();
+            if (tid == 0) { publish_open_sums(); __threadfence(); }
+        }
         if (tid == 0) {
             Slot &sl = slots[scur];
             sl.tile = tile; sl.c_lo = c_lo; sl.c_hi = c_hi; sl.n_own = n_own; sl.ntok = ntok_tile; sl.last_tile = last_tile ? 1 : 0;
@@ -937,14 +955,15 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
             sl.v_tile = sc.v_tile; sl.nbf = sc.nbf >= 0 ? sc.nbf : ntok_tile; sl.end0 = sc.end0; sl.end0_rel = sc.end0_rel;
         }
         PROF(4);
-        if (kWords && want_feats) {
+        if (kFeats) {
             // token-feature mode writes its rows with the prefix in hand (this mode is not pipelined)
-            if (!is_redo) { nb_arrive(BAR_AGG + scur, NTHREADS); nb_sync(BAR_PRE + scur, NTHREADS); }
+            // (named barriers count whole warps: re-converge first, thread 0 has just done single-thread work)
+            if (!is_redo) { __syncwarp(); nb_arrive(BAR_AGG + scur, NTHREADS); nb_sync(BAR_PRE + scur, NTHREADS); }
             const bool need_redo = !is_redo && slots[scur].redo != 0;
             if (!need_redo) {
                 const unsigned long long K_in = slots[scur].K_in;
-        if (kWords && want_feats) {
-            // every split that follows a non-space character ends a token: sum the feature words back to its start
+        if (kFeats) {
+            // every split that follows a non-space character ends a token: sum the feature planes back to its start
             const uint32_t PSr = (Sraw << 1) | ((LB >> 3) & 1u);
             uint32_t ev = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo, last_tile ? c_hi + 1 : c_hi);
             while (ev) {
@@ -958,11 +977,9 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
                     const uint32_t below = SPLIT & mask_lt(i) & ~mask_lt(low);
                     hit = below != 0u;
                     const int sfrom = hit ? 31 - __clz(below) : low;
-                    const uint32_t frag = mask_lt(i) & ~mask_lt(sfrom);
-#pragma unroll
-                    for (int f = 0; f < NFEAT; ++f) acc[f >> 2] += (unsigned)__popc(full[f] & frag) << (8 * (f & 3));   // < 256 each: no carry
+                    plane_sums(mask_lt(i) & ~mask_lt(sfrom), acc);
                 }
-                if (!hit) walk_back(c0 - 1, tid > 0 ? tid - 1 : 0, acc, hit);   // it began in an earlier thread: character by character
+                if (!hit) walk_threads(tid - 1, acc, hit);             // it began in an earlier thread: add the open tails
                 for (long long t = tile - 1; !hit && t >= 0; --t) {      // token began in an earlier tile
                     const uint4 *o = reinterpret_cast<const uint4 *>(p.osum + t);
                     const uint4 a = ld_rec(o), b = ld_rec(o + 1), c4 = ld_rec(o + 2);
@@ -1016,12 +1033,12 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
         }
         int j;   // tile whose outputs are written now
         if (have_work) {
-            if (!(kWords && want_feats)) nb_arrive(BAR_AGG + scur, NTHREADS);
-            j = kWords ? k : k - 1;
+            if (!kFeats) { __syncwarp(); nb_arrive(BAR_AGG + scur, NTHREADS); }
+            j = kSync ? k : k - 1;
             ++k;
-        } else { j = kWords ? -1 : k - 1; drained = true; }
+        } else { j = kSync ? -1 : k - 1; drained = true; }
         if (j >= 0) {
-            if (!(kWords && want_feats)) nb_sync(BAR_PRE + (j & 1), NTHREADS);
+            if (!kFeats) nb_sync(BAR_PRE + (j & 1), NTHREADS);
             if (slots[j & 1].redo) { redo_k = j; continue; }
             emit(j & 1, j % NBUF);
             CBAR();
@@ -1032,38 +1049,50 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
     }
 }
 
-template <bool kDefault, bool kWords>
+template <bool kDefault, bool kWords, bool kFeats>
 static cudaError_t launch_one(const Params &p, int grid, cudaStream_t s)
 {
-    const size_t smem = tokenize_smem_bytes(p.tl, kWords);
+    const size_t smem = tokenize_smem_bytes(p.tl, kWords, kFeats);
     static size_t configured = 0;
     if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(tokenize_kernel<kDefault, kWords>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tokenize_kernel<kDefault, kWords, kFeats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    tokenize_kernel<kDefault, kWords><<<grid, NTHREADS, smem, s>>>(p);
+    tokenize_kernel<kDefault, kWords, kFeats><<<grid, NTHREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words)
+template <bool kDefault, bool kWords, bool kFeats>
+static int ctas_one(const TableLayout &tl)
 {
     int nb = 0;
-    const size_t smem = tokenize_smem_bytes(tl, want_words);
-    cudaError_t e;
-    if (is_default && !want_words) { cudaFuncSetAttribute(tokenize_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<true, false>, NTHREADS, smem); }
-    else if (is_default) { cudaFuncSetAttribute(tokenize_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<true, true>, NTHREADS, smem); }
-    else if (!want_words) { cudaFuncSetAttribute(tokenize_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<false, false>, NTHREADS, smem); }
-    else { cudaFuncSetAttribute(tokenize_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<false, true>, NTHREADS, smem); }
-    if (e != cudaSuccess) { cudaGetLastError(); return 1; }
+    const size_t smem = tokenize_smem_bytes(tl, kWords, kFeats);
+    cudaFuncSetAttribute(tokenize_kernel<kDefault, kWords, kFeats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize_kernel<kDefault, kWords, kFeats>, NTHREADS, smem) != cudaSuccess) { cudaGetLastError(); return 1; }
     return nb < 1 ? 1 : nb;
+}
+
+// v4 runs the token-feature (kFeats) and matrix (kWords) modes; the plain mode is kept for comparison (LATOK_B200_FORCE_V4)
+int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words, bool want_feats)
+{
+    if (is_default) {
+        if (want_words) return want_feats ? ctas_one<true, true, true>(tl) : ctas_one<true, true, false>(tl);
+        return want_feats ? ctas_one<true, false, true>(tl) : ctas_one<true, false, false>(tl);
+    }
+    if (want_words) return want_feats ? ctas_one<false, true, true>(tl) : ctas_one<false, true, false>(tl);
+    return want_feats ? ctas_one<false, false, true>(tl) : ctas_one<false, false, false>(tl);
 }
 
 cudaError_t launch_tokenize(const Params &p, int grid, cudaStream_t s)
 {
-    const bool words = (p.what & (4u | 8u)) != 0u;
-    if (p.rules.is_default) return words ? launch_one<true, true>(p, grid, s) : launch_one<true, false>(p, grid, s);
-    return words ? launch_one<false, true>(p, grid, s) : launch_one<false, false>(p, grid, s);
+    const bool words = (p.what & 8u) != 0u, feats = (p.what & 4u) != 0u;
+    if (p.rules.is_default) {
+        if (words) return feats ? launch_one<true, true, true>(p, grid, s) : launch_one<true, true, false>(p, grid, s);
+        return feats ? launch_one<true, false, true>(p, grid, s) : launch_one<true, false, false>(p, grid, s);
+    }
+    if (words) return feats ? launch_one<false, true, true>(p, grid, s) : launch_one<false, true, false>(p, grid, s);
+    return feats ? launch_one<false, false, true>(p, grid, s) : launch_one<false, false, false>(p, grid, s);
 }
 
 // =====================================================================================================
