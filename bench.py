@@ -220,7 +220,7 @@ def main():
     import torch
     import torch.distributed as dist
     from latok_b200 import _lib
-    from latok_b200.engine import Engine, SPLITS, SPANS
+    from latok_b200.engine import Engine, SPLITS, SPANS, FEATS
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -229,7 +229,8 @@ def main():
     wl = args.workload
     n_strings = args.strings or WORKLOADS[wl]["n"]
     R = max(1, args.resident_batches)
-    what = SPLITS | SPANS
+    classify = wl == "mixed"          # config #4 is quoted with token classification (per-token feature sums) enabled
+    what = SPLITS | SPANS | (FEATS if classify else 0)
     lib = _lib.load()
 
     # ---- synthetic batches (distinct per rank and per resident slot), resident in HBM ----------
@@ -319,11 +320,13 @@ def main():
             self.out_spans, self._p4 = pinned_array(lib, 8 * T0, np.int32)
             self.out_coff, self._p5 = pinned_array(lib, 8 * (S0 + 1), np.int64)
             self.out_toff, self._p6 = pinned_array(lib, 8 * (S0 + 1), np.int64)
+            self.out_feats, self._p7 = pinned_array(lib, 25 * T0 if classify else 16, np.int8)
 
         def step(self):
             _lib.check(lib.latok_b200_submit(self.eng._h, self.pin_b.ctypes.data, self.pin_o.ctypes.data, S0, what))
             _lib.check(lib.latok_b200_fetch(self.eng._h, self.out_splits.ctypes.data, self.out_coff.ctypes.data,
-                                            self.out_spans.ctypes.data, self.out_toff.ctypes.data, None, None))
+                                            self.out_spans.ctypes.data, self.out_toff.ctypes.data,
+                                            self.out_feats.ctypes.data if classify else None, None))
 
     def timed(workers, steps_each):
         for w in workers:
@@ -370,7 +373,7 @@ def main():
     assert np.array_equal(w0.out_spans, w1.out_spans) and np.array_equal(w0.out_toff, w1.out_toff)
     eng2.close()
     h2d = B0 + 8 * (S0 + 1)
-    d2h = C0 + 8 * T0 + 16 * (S0 + 1) + 64
+    d2h = C0 + 8 * T0 + 16 * (S0 + 1) + 64 + (25 * T0 if classify else 0)
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -378,7 +381,7 @@ def main():
         peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg = np.mean([b + c + 8 * t + 16 * (s + 1) for b, c, t, s in stats])
+    alg = np.mean([b + c + 8 * t + 16 * (s + 1) + (25 * t if classify else 0) for b, c, t, s in stats])
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else float("nan")
     achieved = alg / (k_ms * 1e-3) / 1e9
     traffic = None
@@ -398,7 +401,7 @@ def main():
                    "strings_per_gpu": n_strings, "bytes_per_step_per_gpu": int(np.mean([s[0] for s in stats])),
                    "chars_per_step_per_gpu": int(np.mean([s[1] for s in stats])),
                    "tokens_per_step_per_gpu": int(np.mean([s[2] for s in stats])),
-                   "outputs": "int8 split mask + int32 spans + int64 CSR offsets",
+                   "outputs": "int8 split mask + int32 spans + int64 CSR offsets" + (" + int8[T,25] token feature sums" if classify else ""),
                    "l2_hygiene": f"{R} distinct resident batches rotated; per-step footprint "
                                  f"{alg / 1e6:.0f} MB > 126 MB L2",
                    "sharding": "one rank per GPU, independent batches, no data-path collective"},
@@ -408,7 +411,7 @@ def main():
                 "single_engine_value": e2e_single},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "latok::v5::tokenize5_kernel", "kernel_ms": k_ms,
+                     "traffic": traffic, "kernel": "latok::tokenize_kernel<kFeats> (v4)" if classify else "latok::v5::tokenize5_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": float(alg), "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": sampler.summary(),
