@@ -132,6 +132,7 @@ struct latok_b200_engine {
     DevBuf<AggRec> agg;
     DevBuf<IncRec> inc;
     DevBuf<OpenSums> osum;
+    DevBuf<uint32_t> d_planes;
     DevBuf<unsigned long long> span_scratch;
     DevBuf<Result> d_result[2];
     PinBuf<uint8_t> h_in;
@@ -279,7 +280,7 @@ int latok_b200_destroy(latok_b200_engine *e)
     e->d_table.release(); e->d_in.release(); e->d_scratch.release(); e->d_scratch2.release(); e->d_scratch3.release();
     e->d_off.release(); e->d_first[0].release(); e->d_first[1].release(); e->d_char_off.release(); e->d_tok_off.release();
     e->d_splits.release(); e->d_feats.release(); e->d_matrix.release(); e->d_spans.release();
-    e->agg.release(); e->inc.release(); e->osum.release(); e->span_scratch.release();
+    e->agg.release(); e->inc.release(); e->osum.release(); e->d_planes.release(); e->span_scratch.release();
     e->d_result[0].release(); e->d_result[1].release();
     e->h_in.release(); e->h_off.release(); e->h_result[0].release(); e->h_result[1].release();
     if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -325,7 +326,7 @@ static int run_device(latok_b200_engine *e)
     // token-feature / matrix modes run the v4 kernel (one CTA per 7 936-byte tile); split mask + spans run v5 (one warp
     // per 3 968-byte range, V5_NW ranges per tile)
     const bool words = (e->what & LATOK_B200_MATRIX) != 0, feats = (e->what & LATOK_B200_FEATS) != 0;
-    const bool use5 = !words && !feats && !getenv("LATOK_B200_FORCE_V4");
+    const bool use5 = !words && !getenv("LATOK_B200_FORCE_V4");
     const int unit = use5 ? V5_RANGE : TILE;
     const long long nunits = e->n_bytes / unit + 1;
     const long long ntiles = use5 ? (nunits + V5_NW - 1) / V5_NW : nunits;
@@ -334,7 +335,8 @@ static int run_device(latok_b200_engine *e)
     // the status word of every aggregate record carries the launch epoch, so records are zeroed only when (re)allocated
     if ((size_t)ntiles > e->agg.cap) { if (int r = e->agg.ensure((size_t)ntiles, true)) return r; }
     if (int r = e->inc.ensure((size_t)ntiles)) return r;
-    if (e->what & LATOK_B200_FEATS) { if (int r = e->osum.ensure((size_t)ntiles)) return r; }
+    if (feats) { if (int r = e->osum.ensure((size_t)(use5 ? nunits : ntiles), true)) return r; }
+    if (feats && use5) { if (int r = e->d_planes.ensure(tokenize5_plane_words(nunits))) return r; }
     if (int r = e->d_splits.ensure((size_t)e->n_bytes + 64)) return r;
     if (int r = e->d_char_off.ensure((size_t)e->n_strings + 1)) return r;
     if (int r = e->d_tok_off.ensure((size_t)e->n_strings + 1)) return r;
@@ -355,11 +357,11 @@ static int run_device(latok_b200_engine *e)
     p.feats = e->d_feats.p; p.matrix = e->d_matrix.p;
     p.cap_tokens = (long long)(e->d_spans.cap / 2);
     p.what = e->what;
-    p.agg = e->agg.p; p.inc = e->inc.p; p.osum = e->osum.p; p.span_scratch = e->span_scratch.p; p.epoch = e->epoch;
+    p.agg = e->agg.p; p.inc = e->inc.p; p.osum = e->osum.p; p.planes = e->d_planes.p; p.span_scratch = e->span_scratch.p; p.epoch = e->epoch;
     p.ticket = &e->d_result[slot].p->ticket; p.ticket_base = 0;
     p.result = e->d_result[slot].p;
     p.table_blob = e->d_table.p; p.tl = e->tl; p.rules = e->rules;
-    int grid = e->n_sm * (use5 ? tokenize5_ctas_per_sm(e->tl, e->rules.is_default != 0)
+    int grid = e->n_sm * (use5 ? tokenize5_ctas_per_sm(e->tl, e->rules.is_default != 0, feats)
                                : tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words, feats));
     if ((long long)grid > ntiles) grid = (int)ntiles;
     if (!use5) { if (int r = e->span_scratch.ensure((size_t)grid * 2 * SPAN_SCRATCH)) return r; }

@@ -116,6 +116,7 @@ struct Params {
     AggRec *agg;
     IncRec *inc;
     OpenSums *osum;
+    uint32_t *planes;     // v5 token-feature mode: the 25 feature planes of every lane-word, [range][step][25][32 lanes]
     void *span_scratch;   // int2 [grid][2][SPAN_SCRATCH]
     unsigned epoch;
     unsigned long long *ticket;
@@ -128,7 +129,8 @@ struct Params {
 
 size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words, bool want_feats);
 int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words, bool want_feats);
-int tokenize5_ctas_per_sm(const TableLayout &tl, bool is_default);
+int tokenize5_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_feats);
+size_t tokenize5_plane_words(long long nranges);
 cudaError_t launch_tokenize5(const Params &p, int grid, cudaStream_t s);
 cudaError_t launch_tile_index(const long long *offsets, long long n_strings, long long n_bytes,
                               long long *tile_first_str, long long ntiles, int tile_bytes, Result *result, cudaStream_t s);

@@ -108,7 +108,7 @@ __device__ __forceinline__ uint32_t pk_ps(uint32_t k) { return (k >> 30) & 1u; }
 __device__ __forceinline__ int ld_vs32(const int *p) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p))); return v; }
 __device__ __forceinline__ void st_vs32(int *p, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
 
-template <bool kDefault>
+template <bool kDefault, bool kFeats>
 __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_kernel(const Params p)
 {
     constexpr int NC = kDefault ? 3 : 4;      // split-count planes
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         // (only matters when the range owns its very first character, i.e. no closer was found in the head window: such a
         // range is irregular and comes back here with exact = true)
         uint32_t prevLB = 0;
-        if (exact && w0 > 0) {
+        if ((exact || kFeats) && w0 > 0) {       // (token-feature mode: the feature rows of the head-zone characters are summed too)
             const uint8_t *q = X + LPAD - 1;
             int back = 0;
             while (back < 3 && (q[-back] & 0xC0u) == 0x80u) ++back;
@@ -527,6 +527,12 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     for (int i = 0; i < p.rules.n_split; ++i) add1(CNT, NC, term(p.rules.split[i]));
                     for (int i = 0; i < p.rules.n_mask; ++i) Mraw |= term(p.rules.mask[i]);
                     for (int i = 0; i < p.rules.n_sym; ++i) add1(SYC, NY, term(p.rules.sym[i]));
+                }
+                if (kFeats) {
+                    // token-feature mode: the 25 feature planes of the lane-word go to a global scratch for pass D
+                    uint32_t *pl = p.planes + (((size_t)r * RS + js) * NFEAT) * 32 + lane;
+#pragma unroll
+                    for (int f = 0; f < NFEAT; ++f) pl[f * 32] = full[f];
                 }
                 // ---- chunk-aligned ownership (both neighbours look at the same bytes)
                 const uint32_t CLr = (Sraw | Lm_raw) & REAL;
@@ -796,6 +802,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         // range-relative character index of the first character of the string that is open at c_lo (may be negative)
         int cur_base = c_lo - (int)(long long)(G_in - base_in);
         int ktok = 0;                      // tokens of the range before this step
+        unsigned fc[7] = {0, 0, 0, 0, 0, 0, 0};      // token-feature mode: sums of the token open at the end of the previous step
+        bool fc_hit = false;                          // ... and whether its first character has been seen
         const bool spans_direct_all = direct_spans || !closed || !lo_found ||
                                       K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens;   // (the direct path checks every pair)
 #pragma unroll 1
@@ -1006,7 +1014,115 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     __syncwarp();
                 }
             }
+            // ------------------------------------------------------------ per-token feature sums (latok.c:342-354)
+            if (kFeats) {
+                // Every split that follows a non-space character ends a token; the lane that holds it sums the token's
+                // characters back to its first one (a split): population counts of the 25 feature planes over the part
+                // inside this lane-word, then the open tails of the lanes / steps / ranges before it.
+                uint32_t Q[NFEAT];
+                {
+                    const uint32_t *pl = p.planes + (((size_t)r * RS + js) * NFEAT) * 32 + lane;
+#pragma unroll
+                    for (int f = 0; f < NFEAT; ++f) Q[f] = pl[f * 32];
+                }
+                auto plane_sums = [&](uint32_t frag, unsigned acc[7]) {
+#pragma unroll
+                    for (int f = 0; f < NFEAT; ++f) acc[f >> 2] += (unsigned)__popc(Q[f] & frag) << (8 * (f & 3));   // <= 32 each: no carry
+                };
+                uint32_t *tailsS = reinterpret_cast<uint32_t *>(tst);               // [32 lanes][8]: open tail sums + "holds a split"
+                const int high = max(min(n, c_hi - c0), 0);                          // characters below c_hi (head zone included)
+                const uint32_t SPw = SPLIT & mask_lt_nn(high);
+                {
+                    const uint32_t frag = SPw ? (mask_lt_nn(high) & ~mask_lt_nn(31 - __clz(SPw))) : mask_lt_nn(high);
+                    unsigned tl[7] = {0, 0, 0, 0, 0, 0, 0};
+                    plane_sums(frag, tl);
+                    *reinterpret_cast<uint4 *>(tailsS + lane * 8) = make_uint4(tl[0], tl[1], tl[2], tl[3]);
+                    *reinterpret_cast<uint4 *>(tailsS + lane * 8 + 4) = make_uint4(tl[4], tl[5], tl[6], SPw ? 1u : 0u);
+                }
+                __syncwarp();
+                auto add8 = [&](unsigned acc[7], const uint4 &a, const uint4 &b) {
+                    acc[0] = __vadd4(acc[0], a.x); acc[1] = __vadd4(acc[1], a.y); acc[2] = __vadd4(acc[2], a.z); acc[3] = __vadd4(acc[3], a.w);
+                    acc[4] = __vadd4(acc[4], b.x); acc[5] = __vadd4(acc[5], b.y); acc[6] = __vadd4(acc[6], b.z);
+                };
+                // open tails of the lanes below `t`, then of the steps before (fc*), then of the ranges before (osum chain)
+                auto walk_lanes = [&](int t, unsigned acc[7], bool &hit) {
+                    for (; t >= 0 && !hit; --t) {
+                        const uint4 a = *reinterpret_cast<const uint4 *>(tailsS + t * 8), b = *reinterpret_cast<const uint4 *>(tailsS + t * 8 + 4);
+                        add8(acc, a, b);
+                        hit = b.w != 0u;
+                    }
+                    if (!hit) {
+                        add8(acc, make_uint4(fc[0], fc[1], fc[2], fc[3]), make_uint4(fc[4], fc[5], fc[6], 0u));
+                        hit = fc_hit;
+                    }
+                    for (long long rr = r - 1; !hit && rr >= 0; --rr) {            // ranges that do not begin at a closer only
+                        const uint4 *o = reinterpret_cast<const uint4 *>(p.osum + rr);
+                        uint4 h;
+                        unsigned spins = 0;
+                        for (;;) {
+                            h = ld_rec(o);
+                            if (h.y == p.epoch) break;
+                            if (++spins > SPIN_LIMIT) { atomicOr(&p.result->error, 1u); break; }
+                        }
+                        __threadfence();
+                        add8(acc, ld_rec(o + 1), ld_rec(o + 2));
+                        hit = h.x != 0u;
+                    }
+                };
+                {
+                    const uint32_t PSr = (Sraw << 1) | pk_ps(pk);
+                    uint32_t ev = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo + 1, c_hi + 1);
+                    while (ev) {
+                        const int i = __ffs(ev) - 1; ev &= ev - 1;
+                        const long long k = (long long)K_in + ktok + tp + __popc(E & mask_lt_nn(i)) - 1;
+                        if (k < 0 || k >= p.cap_tokens) continue;
+                        unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0};
+                        const uint32_t below = SPLIT & mask_lt_nn(i);
+                        bool hit = below != 0u;
+                        plane_sums(mask_lt_nn(i) & ~mask_lt_nn(hit ? 31 - __clz(below) : 0), acc);
+                        if (!hit) walk_lanes(lane - 1, acc, hit);
+                        // the 25-byte row starts at byte 25 k: whole words where they are ours alone, single bytes at the ends
+                        int8_t *row = p.feats + k * NFEAT;
+                        const int head = (int)((0u - (unsigned)(k & 3)) & 3u);
+                        auto put = [&](int hb) {
+                            for (int q = 0; q < hb; ++q) row[q] = (int8_t)((acc[0] >> (8 * q)) & 0xFFu);
+                            const int nw = (NFEAT - hb) >> 2;
+                            uint32_t *w = reinterpret_cast<uint32_t *>(row + hb);
+#pragma unroll
+                            for (int j = 0; j < 6; ++j)
+                                if (j < nw) w[j] = hb ? __funnelshift_r(acc[j], acc[j + 1], 8 * hb) : acc[j];
+                            for (int q = hb + 4 * nw; q < NFEAT; ++q) row[q] = (int8_t)((acc[q >> 2] >> (8 * (q & 3))) & 0xFFu);
+                        };
+                        if (head == 0) put(0); else if (head == 1) put(1); else if (head == 2) put(2); else put(3);
+                    }
+                }
+                // the token open at the end of this step, for the steps after it (the same walk from the last lane, by all)
+                {
+                    unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0};
+                    bool hit = false;
+                    for (int t = 31; t >= 0 && !hit; --t) {
+                        const uint4 a = *reinterpret_cast<const uint4 *>(tailsS + t * 8), b = *reinterpret_cast<const uint4 *>(tailsS + t * 8 + 4);
+                        add8(acc, a, b);
+                        hit = b.w != 0u;
+                    }
+                    if (!hit) { add8(acc, make_uint4(fc[0], fc[1], fc[2], fc[3]), make_uint4(fc[4], fc[5], fc[6], 0u)); hit = fc_hit; }
+#pragma unroll
+                    for (int g = 0; g < 7; ++g) fc[g] = acc[g];
+                    fc_hit = hit;
+                }
+                __syncwarp();
+            }
             ktok += ntok_step;
+        }
+        if (kFeats) {
+            // the token open at the end of the range, for ranges that do not begin at a chunk closer
+            if (lane == 0) {
+                uint4 *o = reinterpret_cast<uint4 *>(p.osum + r);
+                st_rec(o + 1, make_uint4(fc[0], fc[1], fc[2], fc[3]));
+                st_rec(o + 2, make_uint4(fc[4], fc[5], fc[6], 0u));
+                __threadfence();
+                st_rec(o, make_uint4(fc_hit ? 1u : 0u, p.epoch, 0u, 0u));
+            }
         }
         // ---------------------------------------------------------------- CSR offsets of the strings that start in this range
         // (one lane per string; the character / token counts in front of a byte position come from the parked state)
@@ -1142,39 +1258,47 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     }
 }
 
-template <bool kDefault>
+template <bool kDefault, bool kFeats>
 static cudaError_t launch_one(const Params &p, int grid, cudaStream_t s)
 {
     const size_t smem = (size_t)plan(p.tl, kDefault).total;
     static size_t configured = 0;
     if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(tokenize5_kernel<kDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tokenize5_kernel<kDefault, kFeats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    tokenize5_kernel<kDefault><<<grid, NTH, smem, s>>>(p);
+    tokenize5_kernel<kDefault, kFeats><<<grid, NTH, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+template <bool kDefault, bool kFeats>
+static int ctas_one(const TableLayout &tl)
+{
+    int nb = 0;
+    const size_t smem = (size_t)plan(tl, kDefault).total;
+    cudaFuncSetAttribute(tokenize5_kernel<kDefault, kFeats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tokenize5_kernel<kDefault, kFeats>, NTH, smem) != cudaSuccess) { cudaGetLastError(); return 1; }
+    return nb < 1 ? 1 : nb;
 }
 
 }  // namespace v5
 
 int tokenize5_range_bytes() { return v5::RANGE; }
 int tokenize5_ranges_per_tile() { return v5::NW; }
+size_t tokenize5_plane_words(long long nranges) { return (size_t)nranges * v5::RS * NFEAT * 32; }
 
-int tokenize5_ctas_per_sm(const TableLayout &tl, bool is_default)
+int tokenize5_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_feats)
 {
-    int nb = 0;
-    const size_t smem = (size_t)v5::plan(tl, is_default).total;
-    cudaError_t e;
-    if (is_default) { cudaFuncSetAttribute(v5::tokenize5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v5::tokenize5_kernel<true>, v5::NTH, smem); }
-    else { cudaFuncSetAttribute(v5::tokenize5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, v5::tokenize5_kernel<false>, v5::NTH, smem); }
-    if (e != cudaSuccess) { cudaGetLastError(); return 1; }
-    return nb < 1 ? 1 : nb;
+    if (is_default) return want_feats ? v5::ctas_one<true, true>(tl) : v5::ctas_one<true, false>(tl);
+    return want_feats ? v5::ctas_one<false, true>(tl) : v5::ctas_one<false, false>(tl);
 }
 
 cudaError_t launch_tokenize5(const Params &p, int grid, cudaStream_t s)
 {
-    return p.rules.is_default ? v5::launch_one<true>(p, grid, s) : v5::launch_one<false>(p, grid, s);
+    const bool feats = (p.what & 4u) != 0u;
+    if (p.rules.is_default) return feats ? v5::launch_one<true, true>(p, grid, s) : v5::launch_one<true, false>(p, grid, s);
+    return feats ? v5::launch_one<false, true>(p, grid, s) : v5::launch_one<false, false>(p, grid, s);
 }
 
 }  // namespace latok
