@@ -28,8 +28,10 @@ def engine():
 
 def check_batch(engine, texts, what=ALL, rules=None, label=""):
     if (what & 12) and (what & 3):
-        # split mask + spans alone run the v5 kernel, anything with token features / the matrix the v4 kernel: check both
+        # split mask + spans (+ token features) run the v5 kernel, anything with the matrix the v4 kernel: check them all
         check_batch(engine, texts, what & 3, rules, label + " [splits+spans only]")
+    if (what & 8) and (what & 4):
+        check_batch(engine, texts, what & 7, rules, label + " [v5 with token features]")
     r = engine.run(texts, what)
     o = oracle.tokenize_batch(texts, rules=rules or oracle.DEFAULT_RULES, matrix=bool(what & 8), feats=bool(what & 4))
     assert r.n_chars == o["n_chars"], label
