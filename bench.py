@@ -411,7 +411,7 @@ def main():
                 "single_engine_value": e2e_single},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "latok::tokenize_kernel<kFeats> (v4)" if classify else "latok::v5::tokenize5_kernel", "kernel_ms": k_ms,
+                     "traffic": traffic, "kernel": "latok::v5::tokenize5_kernel<kFeats>" if classify else "latok::v5::tokenize5_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": float(alg), "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": sampler.summary(),
