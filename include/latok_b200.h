@@ -102,6 +102,15 @@ LATOK_B200_API int latok_b200_sizes(latok_b200_engine *e, int64_t *n_chars, int6
  */
 LATOK_B200_API int latok_b200_fetch(latok_b200_engine *e, int8_t *splits, int64_t *char_offsets, int32_t *spans,
                      int64_t *tok_offsets, int8_t *tok_feats, int8_t *matrix);
+/* Token spans as BYTE ranges of the flat UTF-8 buffer, trimmed the way the reference trims a token with
+ * `text[s:e].strip()` (default_tokenizer.py:151-158): utf8[byte_spans[2k] : byte_spans[2k+1]] is the
+ * text of token k, so tokens can be sliced from the packed buffer (or viewed as an Arrow-style string array)
+ * without touching Python strings.  Needs LATOK_B200_SPANS at submit and the submitted text still in place
+ * (host submits: until the next submit; device submits: the caller's buffer).  byte_spans is int64 [T,2] in host
+ * memory, or in device memory when on_device != 0.  Runs three small kernels after the tokenize kernel. */
+LATOK_B200_API int latok_b200_fetch_token_bytes(latok_b200_engine *e, int64_t *byte_spans, int on_device);
+/* device time of those kernels for the last call (harness) */
+LATOK_B200_API int latok_b200_token_bytes_ms(latok_b200_engine *e, float *ms);
 /* Device pointers of the same results (valid until the next submit); for device-side consumers. */
 LATOK_B200_API int latok_b200_device_results(latok_b200_engine *e, const int8_t **splits, const int64_t **char_offsets,
                               const int32_t **spans, const int64_t **tok_offsets,

@@ -47,6 +47,8 @@ def load():
         "latok_b200_submit_device": (C.c_int, [vp, vp, vp, i64, i64, u32]),
         "latok_b200_sizes": (C.c_int, [vp, P(i64), P(i64)]),
         "latok_b200_fetch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+        "latok_b200_fetch_token_bytes": (C.c_int, [vp, vp, i32]),
+        "latok_b200_token_bytes_ms": (C.c_int, [vp, P(C.c_float)]),
         "latok_b200_device_results": (C.c_int, [vp, P(vp), P(vp), P(vp), P(vp), P(vp), P(vp)]),
         "latok_b200_timer_begin": (C.c_int, [vp]),
         "latok_b200_timer_end": (C.c_int, [vp, P(C.c_float)]),

@@ -14,6 +14,7 @@ packed UTF-8 buffer + offsets) goes through one kernel pass and comes back as fl
     featurize_batch(texts) -> list[list[LaToken]]
     split_mask_batch(texts)-> list[int8 arrays]
     batch_arrays(texts, ...) -> engine.BatchResult (splits, spans, CSR offsets, token features)
+    tokenize_packed(buf, offsets) -> PackedTokens (trimmed token byte ranges; .tokens(i), .to_arrow())
 
 Deliberate, documented deviations from the reference:
   * Q5: token feature vectors are the sum over *all* characters of the span; the reference's
@@ -88,6 +89,47 @@ def _token_texts(text: str, spans: np.ndarray) -> List[str]:
 def tokenize_batch(texts: Sequence[str], engine=None) -> List[List[str]]:
     r = batch_arrays(texts, splits=False, spans=True, engine=engine)
     return [_token_texts(t, r.string_spans(i)) for i, t in enumerate(texts)]
+
+
+class PackedTokens:
+    """Tokens of a packed batch as byte ranges of its UTF-8 buffer: the reference's
+    ``text[s:e].strip()`` loop (default_tokenizer.py:151-158) without creating Python strings.
+
+    buf uint8[B]; byte_spans int64[T,2] (trimmed: ``buf[b:e]`` is the token text); tok_offsets int64[S+1]."""
+
+    def __init__(self, buf, byte_spans, tok_offsets):
+        self.buf, self.byte_spans, self.tok_offsets = buf, byte_spans, tok_offsets
+
+    def __len__(self):
+        return len(self.tok_offsets) - 1
+
+    def tokens(self, i: int) -> List[str]:
+        mv = memoryview(self.buf)
+        return [bytes(mv[b:e]).decode("utf-8", "surrogatepass")
+                for b, e in self.byte_spans[self.tok_offsets[i]:self.tok_offsets[i + 1]]]
+
+    def to_arrow(self):
+        """pyarrow ListArray<string>: one list of tokens per input string (token bytes gathered with NumPy)."""
+        import pyarrow as pa
+        ln = self.byte_spans[:, 1] - self.byte_spans[:, 0]
+        off = np.zeros(len(ln) + 1, dtype=np.int64)
+        np.cumsum(ln, out=off[1:])
+        idx = np.repeat(self.byte_spans[:, 0] - off[:-1], ln) + np.arange(off[-1], dtype=np.int64)
+        data = np.ascontiguousarray(self.buf[idx])
+        if off[-1] < 2 ** 31 - 1:
+            values = pa.StringArray.from_buffers(len(ln), pa.py_buffer(off.astype(np.int32)), pa.py_buffer(data))
+            return pa.ListArray.from_arrays(pa.array(self.tok_offsets.astype(np.int32), type=pa.int32()), values)
+        values = pa.LargeStringArray.from_buffers(len(ln), pa.py_buffer(off), pa.py_buffer(data))
+        return pa.LargeListArray.from_arrays(pa.array(self.tok_offsets, type=pa.int64()), values)
+
+
+def tokenize_packed(buf: np.ndarray, offsets: np.ndarray, engine=None) -> PackedTokens:
+    """Packed UTF-8 in (flat uint8 buffer + int64 offsets[S+1]), token byte ranges out; no Python loop per token."""
+    e = engine or default_engine()
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    e.submit(buf, offsets, SPANS)
+    r = e.fetch()
+    return PackedTokens(buf, e.token_bytes(), r.tok_offsets)
 
 
 def featurize_batch(texts: Sequence[str], engine=None) -> List[List[LaToken]]:

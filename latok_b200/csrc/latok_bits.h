@@ -142,6 +142,32 @@ LATOK_HD void squeeze_planes(uint32_t P[NP], uint32_t &F, uint32_t lead, uint32_
     }
 }
 
+// The same result by a five-stage parallel-suffix compress (cost independent of the number of deleted runs):
+// stage i moves every kept bit whose count of deleted positions below it has bit i set down by 2^i.
+#ifndef LATOK_SQUEEZE_RUNS
+#define LATOK_SQUEEZE_RUNS 4      // more deleted runs than this in some lane-word of the warp: use the compress
+#endif
+template <int NP>
+LATOK_HD void squeeze_planes_log(uint32_t P[NP], uint32_t &F, uint32_t lead)
+{
+    F &= lead;
+    if (!lead) return;
+    uint32_t m = lead, mk = ~lead << 1;
+#pragma unroll
+    for (int f = 0; f < NP; ++f) P[f] &= lead;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        uint32_t mp = mk ^ (mk << 1);
+        mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16;
+        const uint32_t mv = mp & m;
+        m = (m ^ mv) | (mv >> (1 << i));
+#pragma unroll
+        for (int f = 0; f < NP; ++f) { const uint32_t t = P[f] & mv; P[f] = (P[f] ^ t) | (t >> (1 << i)); }
+        { const uint32_t t = F & mv; F = (F ^ t) | (t >> (1 << i)); }
+        mk &= ~mp;
+    }
+}
+
 // ---- block mask, common case (latok.c:218-244 when no whitespace chunk holds more than one mark) -------------
 // CL = characters that close a chunk (space / last character of a string), M = marks (never closers under the
 // default rules), cin = a mark is pending in the chunk that is open at the first character.

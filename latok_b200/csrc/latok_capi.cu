@@ -122,7 +122,7 @@ struct latok_b200_engine {
     cudaStream_t stream = nullptr, aux = nullptr;   // aux: string index of the next batch while the previous one is tokenized
     cudaEvent_t ev_in = nullptr, ev_index[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     int slot = 0;                                   // which of the two index / result sets the current batch uses
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
     TableLayout tl{};
     RuleSet rules{};
     DevBuf<uint8_t> d_table, d_in, d_scratch, d_scratch2, d_scratch3;
@@ -134,6 +134,10 @@ struct latok_b200_engine {
     DevBuf<OpenSums> osum;
     DevBuf<uint32_t> d_planes;
     DevBuf<unsigned long long> span_scratch;
+    DevBuf<long long> d_tok_bytes;                  // token byte ranges (latok_b200_fetch_token_bytes)
+    DevBuf<unsigned> d_blk_local, d_group_tot;
+    DevBuf<unsigned long long> d_group_pref;
+    float last_token_bytes_ms = 0.f;
     DevBuf<Result> d_result[2];
     PinBuf<uint8_t> h_in;
     PinBuf<long long> h_off;
@@ -248,6 +252,7 @@ int latok_b200_create(int device, size_t max_batch_bytes, int64_t max_strings, l
             CU(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
         }
         CU(cudaEventCreate(&e->ev_t0)); CU(cudaEventCreate(&e->ev_t1));
+        CU(cudaEventCreate(&e->ev_b0)); CU(cudaEventCreate(&e->ev_b1));
         if (int r = build_table(e)) return r;
         e->rules = default_rules();
         for (int i = 0; i < 2; ++i) {
@@ -281,6 +286,7 @@ int latok_b200_destroy(latok_b200_engine *e)
     e->d_off.release(); e->d_first[0].release(); e->d_first[1].release(); e->d_char_off.release(); e->d_tok_off.release();
     e->d_splits.release(); e->d_feats.release(); e->d_matrix.release(); e->d_spans.release();
     e->agg.release(); e->inc.release(); e->osum.release(); e->d_planes.release(); e->span_scratch.release();
+    e->d_tok_bytes.release(); e->d_blk_local.release(); e->d_group_tot.release(); e->d_group_pref.release();
     e->d_result[0].release(); e->d_result[1].release();
     e->h_in.release(); e->h_off.release(); e->h_result[0].release(); e->h_result[1].release();
     if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -289,6 +295,8 @@ int latok_b200_destroy(latok_b200_engine *e)
     if (e->ev_k0) cudaEventDestroy(e->ev_k0);
     if (e->ev_k1) cudaEventDestroy(e->ev_k1);
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+    if (e->ev_b0) cudaEventDestroy(e->ev_b0);
+    if (e->ev_b1) cudaEventDestroy(e->ev_b1);
     if (e->ev_t1) cudaEventDestroy(e->ev_t1);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -510,6 +518,39 @@ int latok_b200_fetch(latok_b200_engine *e, int8_t *splits, int64_t *char_offsets
     if (tok_feats && T) CU(cudaMemcpyAsync(tok_feats, e->d_feats.p, T * NFEAT, cudaMemcpyDeviceToHost, s));
     if (matrix && C) CU(cudaMemcpyAsync(matrix, e->d_matrix.p, C * NFEAT, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    return LATOK_B200_OK;
+}
+
+int latok_b200_fetch_token_bytes(latok_b200_engine *e, int64_t *byte_spans, int on_device)
+{
+    if (!e) return fail(LATOK_B200_EINVAL, "engine is NULL");
+    if (int r = latok_b200_sizes(e, nullptr, nullptr)) return r;
+    if (!(e->what & LATOK_B200_SPANS)) return fail(LATOK_B200_ESTATE, "spans were not requested at submit");
+    const size_t T = (size_t)e->n_tokens;
+    if (T && !byte_spans) return fail(LATOK_B200_EINVAL, "must specify the byte_spans array (2 * n_tokens entries)");
+    if (!T) return LATOK_B200_OK;
+    long long *d_out = on_device ? (long long *)byte_spans : nullptr;
+    if (!on_device) { if (int r = e->d_tok_bytes.ensure(2 * T)) return r; d_out = e->d_tok_bytes.p; }
+    if (int r = e->d_blk_local.ensure((size_t)token_bytes_blocks(e->n_bytes))) return r;
+    if (int r = e->d_group_tot.ensure((size_t)token_bytes_groups(e->n_bytes))) return r;
+    if (int r = e->d_group_pref.ensure((size_t)token_bytes_groups(e->n_bytes))) return r;
+    cudaStream_t s = e->stream;
+    CU(cudaEventRecord(e->ev_b0, s));
+    CU(launch_token_bytes(e->cur_in, e->n_bytes, e->cur_off, e->d_char_off.p, e->d_tok_off.p, e->n_strings, e->d_spans.p,
+                          d_out, e->d_blk_local.p, e->d_group_tot.p, e->d_group_pref.p, e->d_table.p, e->tl, e->n_sm, s));
+    CU(cudaEventRecord(e->ev_b1, s));
+    e->launches += 3;
+    if (!on_device) CU(cudaMemcpyAsync(byte_spans, d_out, T * 2 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev_b0, e->ev_b1) == cudaSuccess) e->last_token_bytes_ms = ms; else cudaGetLastError();
+    return LATOK_B200_OK;
+}
+
+int latok_b200_token_bytes_ms(latok_b200_engine *e, float *ms)
+{
+    if (!e || !ms) return fail(LATOK_B200_EINVAL, "engine or ms is NULL");
+    *ms = e->last_token_bytes_ms;
     return LATOK_B200_OK;
 }
 

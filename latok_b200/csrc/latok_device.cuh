@@ -409,6 +409,26 @@ __device__ __forceinline__ uint32_t mb_entry(const uint8_t *p, const Tables &t, 
     return (cp >= t.high_first && cp <= t.high_last) ? 256u + high_class : 256u;
 }
 
+// Feature word of the multi-byte character whose four bytes (lead byte >= 0xC0 in the low byte, then up to three
+// continuation bytes; whatever follows a shorter character is ignored) are `v` -- the same decode and look-up as
+// mb_entry + the feature tables, without the length branches, so that lanes holding 2-, 3- and 4-byte characters
+// stay converged and two characters can be in flight at once.
+__device__ __forceinline__ uint32_t mb_features(uint32_t v, const Tables &t)
+{
+    const int L = __clz((int)~(v << 24)) - 1;                  // continuation bytes: 1..3 (>= 4: invalid lead byte)
+    const uint32_t c1 = (v >> 8) & 0x3Fu, c2 = (v >> 16) & 0x3Fu, c3 = (v >> 24) & 0x3Fu;
+    const uint32_t cp4 = ((v & (0x3Fu >> L)) << 18) | (c1 << 12) | (c2 << 6) | c3;
+    const uint32_t cp = cp4 >> (6 * (3 - L) & 31);
+    const uint32_t cl = min(cp, t.low_limit - 1u);
+    const uint32_t blk = t.stage1[cl >> 7];
+    const uint32_t b = t.stage2[blk * 64u + ((cl & 127u) >> 1)];
+    uint32_t fw = t.class_feat[(b >> ((cl & 1u) * 4u)) & 15u];
+    if (cp >= t.low_limit) fw = (cp >= t.high_first && cp <= t.high_last) ? t.high_feat : 0u;
+    if (cp < 0x80u) fw = t.ascii_feat[cp];                     // over-long form of an ASCII character
+    if (L > 3) fw = 0u;                                        // 0xF8..0xFF: no features
+    return fw;
+}
+
 // Backlog through one thread's characters (latok.c:218-244 in scan form): x += 1 at a mark, x = 0 at a
 // string start, a closer (space / end of string) is "hot" if x >= 1 when it is reached, a space then takes
 // one off and the end of a string clears it.  Driven by the (rare) marks; closers are only visited while x > 0.

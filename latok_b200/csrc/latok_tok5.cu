@@ -425,16 +425,41 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 sbmS[j * 32 + lane] = leadc;                            // from here on the slot holds the lead-byte mask
                 uint32_t mm = b[7] & b[6] & valid;                      // lead bytes of multi-byte characters
                 classify_ascii(b, Pc);
-                while (mm) {
-                    const int k = __ffs(mm) - 1; mm &= mm - 1;
-                    const uint32_t e = mb_entry(src + k, tb, p.tl.high_class);
-                    const uint32_t fw = e < 256u ? (e < 128u ? tb.ascii_feat[e] : 0u) : tb.class_feat[e - 256u];
-                    const uint32_t bitk = 1u << k;
-#pragma unroll
-                    for (int f = 0; f < NBASE; ++f) if (fw & (1u << f)) Pc[f] |= bitk;
-                }
+                // multi-byte characters: decode + class table, features patched in at the lead byte, then the continuation
+                // bytes are squeezed out.  Sparse (at most one such character per lane-word, e.g. an emoji in a tweet): one
+                // look-up, run-by-run squeeze.  Dense (accented Latin, CJK): two characters per trip (independent look-up
+                // chains, no branch on the character's length) and a five-stage compress.
+                auto four_bytes = [&](int k) -> uint32_t {
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(src + (k & ~3));
+                    return __funnelshift_r(w[0], w[1], 8 * (k & 3));
+                };
                 Fc = sb;
-                squeeze_planes<NBASE>(Pc, Fc, leadc, valid);
+                if (!__any_sync(FULL, (mm & (mm - 1u)) != 0u)) {
+                    if (mm) {
+                        const int k = __ffs(mm) - 1;
+                        const uint32_t fw = mb_features(four_bytes(k), tb), bitk = 1u << k;
+#pragma unroll
+                        for (int f = 0; f < NBASE; ++f) if (fw & (1u << f)) Pc[f] |= bitk;
+                    }
+                    squeeze_planes<NBASE>(Pc, Fc, leadc, valid);
+                } else {
+                    while (mm) {
+                        const int k0 = __ffs(mm) - 1; mm &= mm - 1;
+                        const bool two = mm != 0u;
+                        const int k1 = two ? __ffs(mm) - 1 : k0; mm &= mm - 1;
+                        const uint32_t v0 = four_bytes(k0), v1 = four_bytes(k1);
+                        const uint32_t fw0 = mb_features(v0, tb), fw1 = two ? mb_features(v1, tb) : 0u;
+                        const uint32_t bit0 = 1u << k0, bit1 = 1u << k1;
+#pragma unroll
+                        for (int f = 0; f < NBASE; ++f) {
+                            if (fw0 & (1u << f)) Pc[f] |= bit0;
+                            if (fw1 & (1u << f)) Pc[f] |= bit1;
+                        }
+                    }
+                    const uint32_t del = leadc ? (~leadc & valid) : 0u;
+                    if (__any_sync(FULL, __popc(del & ~(del >> 1)) > LATOK_SQUEEZE_RUNS)) squeeze_planes_log<NBASE>(Pc, Fc, leadc);
+                    else squeeze_planes<NBASE>(Pc, Fc, leadc, valid);
+                }
                 nc = __popc(leadc);
                 int sc = nc;
 #pragma unroll

@@ -156,6 +156,24 @@ class Engine:
         r.kernel_ms, r.lookahead_walks = ms.value, walks.value
         return r
 
+    def token_bytes(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """int64 [T,2] byte ranges of the tokens of the last batch in its flat UTF-8 buffer, trimmed like the
+        reference's `text[s:e].strip()` (default_tokenizer.py:151-158): `buf[b:e]` is the token text."""
+        if not self._what & SPANS:
+            raise RuntimeError("spans were not requested at submit")
+        _, n_tokens = self.sizes()
+        if out is None:
+            out = np.empty((n_tokens, 2), dtype=np.int64)
+        if out.dtype != np.int64 or out.shape != (n_tokens, 2) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous int64 array of shape (n_tokens, 2)")
+        _lib.check(self._L.latok_b200_fetch_token_bytes(self._h, out.ctypes.data if n_tokens else None, 0))
+        return out
+
+    def token_bytes_ms(self) -> float:
+        ms = C.c_float(0)
+        _lib.check(self._L.latok_b200_token_bytes_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def run(self, texts: Sequence[str], what: int = SPLITS | SPANS) -> BatchResult:
         buf, offsets = pack_strings(texts)
         self.submit(buf, offsets, what)

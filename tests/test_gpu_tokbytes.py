@@ -1,0 +1,78 @@
+"""Token spans as trimmed byte ranges of the packed UTF-8 buffer against the reference's token
+texts: the committed outputs of the reference's own tokenize() (tests/golden/reference_outputs.json) and the
+oracle's restatement of `text[s:e].strip()` (default_tokenizer.py:151-158).  Needs a B200 (-m gpu)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import corpus
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from latok_b200.engine import Engine
+    with Engine(0) as e:
+        yield e
+
+
+def _packed(engine, texts):
+    from latok_b200.core.default_tokenizer import tokenize_packed
+    from latok_b200.engine import pack_strings
+    buf, off = pack_strings(texts)
+    return tokenize_packed(buf, off, engine=engine)
+
+
+def test_golden_token_texts(engine):
+    recs = json.loads((Path(__file__).parent / "golden" / "reference_outputs.json").read_text())["records"]
+    recs = [r for r in recs if r["text"]]
+    pt = _packed(engine, [r["text"] for r in recs])
+    for i, r in enumerate(recs):
+        assert pt.tokens(i) == r["tokens"], r["text"]
+
+
+@pytest.mark.parametrize("profile,seed", [("mixed", 11), ("ascii", 12), ("mixed", 13)])
+def test_fuzz_token_texts(engine, profile, seed):
+    texts = [t for t in corpus.fuzz_strings(seed, 1500, 200, profile) if t] + corpus.FIXTURES
+    texts = [t for t in texts if t]
+    pt = _packed(engine, texts)
+    for i, t in enumerate(texts):
+        assert pt.tokens(i) == oracle.tokens(t), t
+
+
+def test_long_multibyte_strings_cross_blocks(engine):
+    # strings far longer than the 512-byte counting blocks and the 128 KB scan groups, with every UTF-8 length
+    rng = np.random.default_rng(5)
+    alphabet = ["a", "B", " ", "é", "日", "😀", ",", "　", "@", "x", "ß", " ", "1"]
+    texts = ["".join(rng.choice(alphabet, size=n)) for n in (5000, 70000, 300000, 3)]
+    pt = _packed(engine, texts)
+    for i, t in enumerate(texts):
+        assert pt.tokens(i) == oracle.tokens(t)
+
+
+def test_arrow_view_and_edge_cases(engine):
+    texts = ["This is a #test!", "", " ", "a", "日本語 のテキスト、です。", "x" * 1000 + " y"]
+    pt = _packed(engine, texts)
+    want = [oracle.tokens(t) if t else [] for t in texts]
+    assert [pt.tokens(i) for i in range(len(texts))] == want
+    assert pt.to_arrow().to_pylist() == want
+    # every range lies inside its string and ranges are ordered and disjoint
+    from latok_b200.engine import pack_strings
+    _, off = pack_strings(texts)
+    for i in range(len(texts)):
+        sp = pt.byte_spans[pt.tok_offsets[i]:pt.tok_offsets[i + 1]]
+        assert np.all(sp[:, 0] < sp[:, 1]) and np.all(sp[1:, 0] >= sp[:-1, 1])
+        if len(sp):
+            assert sp[0, 0] >= off[i] and sp[-1, 1] <= off[i + 1]
+
+
+def test_needs_spans(engine):
+    from latok_b200.engine import SPLITS, pack_strings
+    buf, off = pack_strings(["abc def"])
+    engine.submit(buf, off, SPLITS)
+    with pytest.raises(RuntimeError):
+        engine.token_bytes()

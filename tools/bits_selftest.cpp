@@ -49,6 +49,9 @@ int main()
         squeeze_planes<3>(Q, G, lead, vmask);
         const uint32_t nm = bits_low(o);
         if (lead) CHECK((Q[0] & nm) == wantP[0] && (Q[1] & nm) == wantP[1] && (Q[2] & nm) == wantP[2] && (G & nm) == wantF, "squeeze lead %08X", lead);
+        uint32_t R[3] = {P[0], P[1], P[2]}, H = F;
+        squeeze_planes_log<3>(R, H, lead);
+        if (lead) CHECK(R[0] == wantP[0] && R[1] == wantP[1] && R[2] == wantP[2] && H == wantF, "squeeze (compress form) lead %08X", lead);
     }
     // chunk_carry / flood_down against the sequential definition (at most one mark per chunk, else just the DUP flag)
     for (int rep = 0; rep < 200000; ++rep) {
