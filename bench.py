@@ -34,12 +34,23 @@ WORKLOADS = {
     "tweets": dict(desc="config#2: 1M synthetic tweet-sized strings (~140 chars, ASCII-heavy), seed 20240601", n=1_000_000),
     "mixed": dict(desc="config#4: 1M mixed-Unicode strings (~160 chars), seed 20240603", n=1_000_000),
     "docs": dict(desc="config#3: long documents of 64 KB, seed 20240602", n=20_000),
+    # strong scaling: ONE batch of ~1e9 characters, cut into byte-balanced ranges of whole strings, one range per rank
+    "chars1b": dict(desc="config#5: 1B-character batch of config-#2 text (7.1M strings, seeds 20240605+) sharded by "
+                         "byte-balanced string ranges", n=7_100_000),
 }
-CPU_SAMPLE_STRINGS = {"tweets": 200_000, "mixed": 200_000, "docs": 200}
+CPU_SAMPLE_STRINGS = {"tweets": 200_000, "mixed": 200_000, "docs": 200, "chars1b": 200_000}
 
 
 def make_batch(workload: str, n: int, seed_shift: int):
     from latok_b200 import synth
+    if workload == "chars1b":      # the whole batch (every rank builds the same one and keeps its own range)
+        bufs, offs, base, k = [], [np.zeros(1, dtype=np.int64)], 0, 0
+        while n > 0:
+            m = min(n, 1_000_000)
+            b, o = synth.tweets(m, 20240605 + k)
+            bufs.append(b); offs.append(o[1:] + base)
+            base += len(b); n -= m; k += 1
+        return np.concatenate(bufs), np.concatenate(offs)
     if workload == "tweets":
         return synth.tweets(n, 20240601 + seed_shift)
     if workload == "mixed":
@@ -200,7 +211,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tweets", choices=list(WORKLOADS))
-    ap.add_argument("--strings", type=int, default=0, help="override strings per GPU (smaller = NOT the named config)")
+    ap.add_argument("--strings", type=int, default=0, help="override strings per GPU -- chars1b: of the whole batch -- (smaller = NOT the named config)")
     ap.add_argument("--resident-batches", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 10)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -234,7 +245,18 @@ def main():
     lib = _lib.load()
 
     # ---- synthetic batches (distinct per rank and per resident slot), resident in HBM ----------
-    host = [make_batch(wl, n_strings, 1000 * rank + r) for r in range(R)]
+    strong = wl == "chars1b"
+    if strong:
+        from latok_b200.sharding import shard_ranges, slice_shard
+        fb, fo = make_batch(wl, n_strings, 0)
+        s0, s1 = shard_ranges(fo, world)[rank]
+        b, o = slice_shard(fb, fo, s0, s1)
+        host = [(np.ascontiguousarray(b), np.ascontiguousarray(o))]
+        R = 1                         # one resident batch: a rank's range is far larger than the 126 MB L2
+        n_strings = s1 - s0
+        del fb, fo
+    else:
+        host = [make_batch(wl, n_strings, 1000 * rank + r) for r in range(R)]
     dev = [(torch.from_numpy(b.copy()).cuda(), torch.from_numpy(o.copy()).cuda()) for b, o in host]
     eng = Engine(local_rank, max(len(b) for b, _ in host) + 4096, n_strings + 1)
 
@@ -396,15 +418,17 @@ def main():
         "metric": "tokenized_text_throughput", "value": value, "unit": "GB/s",
         "strings_per_s": total_strings / (elapsed_ms * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOADS[wl]["desc"] + (f" [OVERRIDE strings={n_strings}]" if args.strings else ""),
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOADS[wl]["desc"] + (f" [OVERRIDE strings={args.strings}]" if args.strings else ""),
                    "strings_per_gpu": n_strings, "bytes_per_step_per_gpu": int(np.mean([s[0] for s in stats])),
                    "chars_per_step_per_gpu": int(np.mean([s[1] for s in stats])),
                    "tokens_per_step_per_gpu": int(np.mean([s[2] for s in stats])),
                    "outputs": "int8 split mask + int32 spans + int64 CSR offsets" + (" + int8[T,25] token feature sums" if classify else ""),
                    "l2_hygiene": f"{R} distinct resident batches rotated; per-step footprint "
                                  f"{alg / 1e6:.0f} MB > 126 MB L2",
-                   "sharding": "one rank per GPU, independent batches, no data-path collective"},
+                   "sharding": ("one rank per GPU on its byte-balanced range of whole strings of the ONE batch, no data-path "
+                                "collective, one all-gather of the per-rank token counts" if strong else
+                                "one rank per GPU, independent batches, no data-path collective")},
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps_done, "strings_per_s": world * S0 * e2e_steps_done / e2e_s,
                 "mode": "double-buffered: 2 engines x 1 host thread per GPU, pinned host buffers, submit + fetch per step",

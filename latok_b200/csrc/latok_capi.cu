@@ -529,14 +529,15 @@ int latok_b200_fetch_token_bytes(latok_b200_engine *e, int64_t *byte_spans, int 
     const size_t T = (size_t)e->n_tokens;
     if (T && !byte_spans) return fail(LATOK_B200_EINVAL, "must specify the byte_spans array (2 * n_tokens entries)");
     if (!T) return LATOK_B200_OK;
+    if (on_device && ((uintptr_t)byte_spans & 15u) != 0) return fail(LATOK_B200_EINVAL, "a device byte_spans array must be 16-byte aligned");
     long long *d_out = on_device ? (long long *)byte_spans : nullptr;
     if (!on_device) { if (int r = e->d_tok_bytes.ensure(2 * T)) return r; d_out = e->d_tok_bytes.p; }
-    if (int r = e->d_blk_local.ensure((size_t)token_bytes_blocks(e->n_bytes))) return r;
+    if (int r = e->d_blk_local.ensure((size_t)token_bytes_words(e->n_bytes))) return r;
     if (int r = e->d_group_tot.ensure((size_t)token_bytes_groups(e->n_bytes))) return r;
     if (int r = e->d_group_pref.ensure((size_t)token_bytes_groups(e->n_bytes))) return r;
     cudaStream_t s = e->stream;
     CU(cudaEventRecord(e->ev_b0, s));
-    CU(launch_token_bytes(e->cur_in, e->n_bytes, e->cur_off, e->d_char_off.p, e->d_tok_off.p, e->n_strings, e->d_spans.p,
+    CU(launch_token_bytes(e->cur_in, e->n_bytes, e->cur_off, e->d_char_off.p, e->d_tok_off.p, e->n_strings, e->n_tokens, e->d_spans.p,
                           d_out, e->d_blk_local.p, e->d_group_tot.p, e->d_group_pref.p, e->d_table.p, e->tl, e->n_sm, s));
     CU(cudaEventRecord(e->ev_b1, s));
     e->launches += 3;

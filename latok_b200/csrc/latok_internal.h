@@ -142,11 +142,11 @@ cudaError_t launch_combine_rows(const int8_t *m, long long m_rows, long long m_c
                                 int8_t *out, cudaStream_t s);
 
 // token spans as trimmed byte ranges of the flat buffer (latok_tokbytes.cu)
-long long token_bytes_blocks(long long n_bytes);
+long long token_bytes_words(long long n_bytes);
 long long token_bytes_groups(long long n_bytes);
 cudaError_t launch_token_bytes(const uint8_t *in, long long n_bytes, const long long *offsets, const long long *char_off,
-                               const long long *tok_off, long long n_strings, const int32_t *spans, long long *out,
-                               unsigned *blk_local, unsigned *group_tot, unsigned long long *group_pref,
+                               const long long *tok_off, long long n_strings, long long n_tokens, const int32_t *spans,
+                               long long *out, unsigned *word_local, unsigned *group_tot, unsigned long long *group_pref,
                                const uint8_t *table_blob, const TableLayout &tl, int n_sm, cudaStream_t s);
 
 }  // namespace latok

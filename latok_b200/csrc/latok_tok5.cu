@@ -182,8 +182,17 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 // the fast evaluation does not apply (a chunk with several marks, or one that is open at a range boundary):
                 // take the exact prefix first, then evaluate once with the backlog that really enters; nothing is published
                 // for this tile until then, so the tiles after it wait
+#ifdef LATOK_PROFILE
+                const long long _s0 = clock64();
+#endif
                 pre = lookback(tile, p, lane);
+#ifdef LATOK_PROFILE
+                const long long _s1 = clock64();
+#endif
                 order_exact(pre.x); gather();
+#ifdef LATOK_PROFILE
+                if (lane == 0) { atomicAdd(&p.result->prof[9], (unsigned long long)(_s1 - _s0)); atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
+#endif
                 if (lane == 0) atomicAdd(&p.result->prof[15], 1ull);
             } else {
                 const unsigned ylf = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
@@ -193,7 +202,15 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     st_rec(p.agg + tile, r);
                 }
                 pre = lookback(tile, p, lane);
-                if (pre.x != 0) { order_exact(pre.x); gather(); }
+                if (pre.x != 0) {
+#ifdef LATOK_PROFILE
+                    const long long _s1 = clock64();
+#endif
+                    order_exact(pre.x); gather();
+#ifdef LATOK_PROFILE
+                    if (lane == 0) { atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
+#endif
+                }
             }
             if (lane == 0) {
                 IncRec *ir = p.inc + tile;

@@ -23,7 +23,7 @@ with Engine(0) as e:
         ms = C.c_float(0); w = C.c_int64(0)
         _lib.check(_lib.load().latok_b200_last_stats(e._h, C.byref(ms), C.byref(w)))
         if i == 0 and what & 2:
-            e.token_bytes()
+            e.token_bytes(); e.token_bytes()        # (the first call pays for loading the kernels)
             print(f"token byte ranges: {e.token_bytes_ms():.3f} ms ({(len(buf) + 24 * t + 40 * len(off)) / e.token_bytes_ms() / 1e6:.1f} GB/s algorithmic)")
         alg = len(buf) + c + 8 * t + 16 * (len(off))
         print(f"{wl} S={len(off)-1} B={len(buf)} C={c} T={t} kernel={ms.value:.3f} ms  in={len(buf)/ms.value/1e6:.1f} GB/s  alg={alg/ms.value/1e6:.1f} GB/s ({alg/ms.value/1e6/6545.9*100:.1f}% of 6545.9) walks={w.value}")
