@@ -173,52 +173,83 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x0020
 // bit-exact (latok.c:218-244 has unbounded reach).
 static __device__ bool walk_ahead(const Params &p, const Tables &t, long long pos0, int lane)
 {
-    // end of the string that contains pos0: first offset > pos0
-    long long e = p.n_bytes;
-    if (lane == 0) {
-        long long lo = 0, hi = p.n_strings;  // offsets[lo] <= pos0 < offsets[hi] invariant target
-        while (lo < hi) {
-            long long mid = (lo + hi) >> 1;
-            if (p.offsets[mid] > pos0) hi = mid; else lo = mid + 1;
-        }
-        e = p.offsets[lo <= p.n_strings ? lo : p.n_strings];
-    }
-    e = __shfl_sync(0xFFFFFFFFu, e, 0);
     const uint8_t *in = p.in;
-    auto byte_at = [&](long long q) -> uint32_t { return (q >= 0 && q < p.n_bytes) ? (uint32_t)in[q] : 0u; };
-    auto is_lead = [&](long long q) -> bool { return (byte_at(q) & 0xC0u) != 0x80u; };
+    // end of the string that contains pos0: first offset > pos0 (32 probes per round)
+    long long e;
+    {
+        long long lo = 0, hi = p.n_strings;              // the answer is in [lo, hi]; offsets[n_strings] = n_bytes > pos0
+        while (lo < hi) {
+            const long long step = (hi - lo + 31) / 32;
+            const long long c = lo + step * lane;
+            const bool gt = c >= hi || p.offsets[c] > pos0;       // monotone over the lanes
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, gt);
+            if (b == 0u) lo = lo + 31 * step + 1;
+            else {
+                const int f = __ffs(b) - 1;
+                const long long nh = lo + step * f;
+                if (f > 0) lo = lo + step * (f - 1) + 1;
+                hi = nh < hi ? nh : hi;
+            }
+        }
+        e = p.offsets[lo];
+    }
     struct G { const uint8_t *in; long long q, n; __device__ uint32_t operator[](int k) const { long long a = q + k; return a < n ? (uint32_t)in[a] : 0u; } };
+    // the character in front of pos0 (we are strictly inside the string, so it exists)
+    uint32_t prev_w;
+    {
+        long long pp = pos0 - 1;
+        for (int k = 0; k < 8 && pp > 0 && (in[pp] & 0xC0u) == 0x80u; ++k) --pp;
+        prev_w = classify_at(G{in, pp, p.n_bytes}, t);
+    }
+    // 32 bytes per trip, one byte per lane; the rules are evaluated for the characters that begin in the first ZONE
+    // bytes (their next and after-next characters begin inside the 32 bytes), then the window moves on by ZONE
+    constexpr int ZONE = 24, AHEAD = 4;
     bool any = false;
-    for (long long q = pos0; q < e; q += 32) {
-        long long pos = q + lane;
-        bool lead = pos < e && is_lead(pos);
+    for (long long q0 = pos0; q0 < e; q0 += AHEAD * ZONE) {
+      // the bytes of AHEAD windows are fetched together (the walk runs into text nobody has touched yet: DRAM latency)
+      uint32_t bytes[AHEAD];
+#pragma unroll
+      for (int g = 0; g < AHEAD; ++g) {
+          const long long pos = q0 + g * ZONE + lane;
+          bytes[g] = pos < e ? (uint32_t)in[pos] : 0x80u;
+      }
+#pragma unroll
+      for (int g = 0; g < AHEAD; ++g) {
+        const long long q = q0 + g * ZONE;
+        if (q >= e) break;
+        const long long pos = q + lane;
+        const bool inb = pos < e;
+        const uint32_t byte = bytes[g];
+        const bool lead = inb && (byte & 0xC0u) != 0x80u;
+        const unsigned leads = __ballot_sync(0xFFFFFFFFu, lead);
+        uint32_t w = 0;
+        if (lead) w = byte < 0x80u ? (uint32_t)t.ascii_feat[byte] : classify_at(G{in, pos, p.n_bytes}, t);
+        const unsigned above = lane == 31 ? 0u : (leads & (0xFFFFFFFFu << (lane + 1)));
+        const unsigned above2 = above & (above - 1u);
+        const unsigned below = leads & ((1u << lane) - 1u);
+        const uint32_t nw = __shfl_sync(0xFFFFFFFFu, w, above ? __ffs(above) - 1 : 0);
+        const uint32_t aw = __shfl_sync(0xFFFFFFFFu, w, above2 ? __ffs(above2) - 1 : 0);
+        uint32_t pw = __shfl_sync(0xFFFFFFFFu, w, below ? 31 - __clz(below) : 0);
+        if (!below) pw = prev_w;
+        const bool has_next = above != 0u, has_an = above2 != 0u;
         bool closer = false, mk = false;
-        if (lead) {
-            uint32_t w = classify_at(G{in, pos, p.n_bytes}, t);
-            // previous character (we are strictly inside the string, so it exists)
-            long long pp = pos - 1;
-            for (int k = 0; k < 8 && pp > 0 && !is_lead(pp); ++k) --pp;
-            uint32_t pw = classify_at(G{in, pp, p.n_bytes}, t);
-            long long n1 = pos + 1;
-            for (int k = 0; k < 8 && n1 < e && !is_lead(n1); ++k) ++n1;
-            bool has_next = n1 < e;
-            uint32_t nw = has_next ? classify_at(G{in, n1, p.n_bytes}, t) : 0u;
-            long long n2 = n1 + 1;
-            for (int k = 0; k < 8 && n2 < e && !is_lead(n2); ++k) ++n2;
-            bool has_an = has_next && n2 < e;
-            uint32_t aw = has_an ? classify_at(G{in, n2, p.n_bytes}, t) : 0u;
-            uint32_t full = make_word(pw, w, nw, aw, false, !has_next, !has_an);
+        const bool ev = lead && lane < ZONE;
+        if (ev) {
+            const uint32_t full = make_word(pw, w, nw, aw, false, !has_next, !has_an);
             uint32_t cnt, sy;
             eval_rules(p.rules, full, cnt, mk, sy);
             closer = ((full >> 5) & 1u) || !has_next;
         }
-        unsigned bc = __ballot_sync(0xFFFFFFFFu, closer), bm = __ballot_sync(0xFFFFFFFFu, lead && mk);
+        const unsigned bc = __ballot_sync(0xFFFFFFFFu, ev && closer), bm = __ballot_sync(0xFFFFFFFFu, ev && mk);
         if (bc) {
-            int first = __ffs(bc) - 1;
+            const int first = __ffs(bc) - 1;
             return any || (bm & (first == 31 ? 0xFFFFFFFFu : ((2u << first) - 1u))) != 0u;
         }
         any = any || bm != 0u;
         if (any) return true;
+        const unsigned zone = leads & ((1u << ZONE) - 1u);
+        if (zone) prev_w = __shfl_sync(0xFFFFFFFFu, w, 31 - __clz(zone));
+      }
     }
     return any;
 }

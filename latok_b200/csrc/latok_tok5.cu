@@ -53,7 +53,9 @@ struct WAgg { int n_own, ntok, lft, v, flags, pad[3]; };
 struct Slot { unsigned long long G, K, base; int mode, x_in; };
 struct RInfo { int c_lo, c_hi, n_own, ntok, flags, pad[3]; };    // flags: 1 have, 2 closed, 4 lo_found, 8 last_range
 struct Ctl {
-    int tile_id[2], tk_cnt[2], tk_flag[2], pad0[2];
+    int tile_id[2], tk_cnt[2], tk_flag[2];
+    int xr[2];                           // exact evaluation: the round for which slot[].x_in (the backlog entering the tile) is valid
+    int pad0[2];
     Slot slot[2];
     WAgg wagg[2][NW];
     int xfu[NW], xfv[NW];                // exact evaluation: backlog transfer function of every range of the tile
@@ -95,6 +97,15 @@ __host__ __device__ inline Plan plan(const TableLayout &tl, bool is_default)
 #define PROF5(i) do { } while (0)
 #endif
 
+// LATOK_PROFX builds: where the time of the EXACT evaluation goes (summed clock64() deltas of every compute warp):
+// prof[0] string map + pass A, [1] transfer functions, [2] wait for the backlog, [3] mark-by-mark pass, [4] look-ahead
+// walk, [5] pass C, [6] window reload, [7] number of exact range evaluations
+#ifdef LATOK_PROFX
+#define PROFX(i) do { if (exact && lane == 0) { long long _t = clock64(); atomicAdd(&p.result->prof[i], (unsigned long long)(_t - _px)); _px = _t; } } while (0)
+#else
+#define PROFX(i) do { } while (0)
+#endif
+
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int CINF = 0x3FFFFFFF;
 
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         if (threadIdx.x == 0) {
             for (int w = 0; w < 2 * NW; ++w) mbar_init(mbar + w, 1);
             for (int w = 0; w < NW; ++w) { ctl.xfu[w] = 0; ctl.xfv[w] = 0; ctl.xfgen[w] = 0; }
-            for (int b = 0; b < 2; ++b) { ctl.tile_id[b] = 0; ctl.tk_cnt[b] = 0; ctl.tk_flag[b] = 0; }
+            for (int b = 0; b < 2; ++b) { ctl.tile_id[b] = 0; ctl.tk_cnt[b] = 0; ctl.tk_flag[b] = 0; ctl.xr[b] = 0; }
         }
     }
     __syncthreads();
@@ -165,13 +176,24 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 v = __shfl_sync(FULL, a.v, NW - 1);
                 irregular = __any_sync(FULL, lane < NW && (a.flags & 1));
             };
-            auto order_exact = [&](int x_in) {
+            // the compute warps are told to run the exact evaluation; the backlog that enters the tile may follow later
+            // (give_backlog): reload, pass A and the ranges' transfer functions do not need it
+            auto give_backlog = [&](int x_in) {
+                if (lane == 0) {
+                    st_vs32(&ctl.slot[s].x_in, x_in);
+                    __threadfence_block();
+                    st_vs32(&ctl.xr[s], (int)round);
+                }
+                __syncwarp();
+            };
+            auto order_exact = [&](int x_in, bool known) {
                 ++round;
                 if (lane == 0) {
-                    ctl.slot[s].mode = 1; ctl.slot[s].x_in = x_in;
+                    ctl.slot[s].mode = 1;
                     __threadfence_block();
                 }
                 __syncwarp();
+                if (known) give_backlog(x_in);
                 nb_arrive(BAR_PRE + s, NTH);
             };
             gather();
@@ -180,16 +202,18 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             Prefix pre;
             if (irregular) {
                 // the fast evaluation does not apply (a chunk with several marks, or one that is open at a range boundary):
-                // take the exact prefix first, then evaluate once with the backlog that really enters; nothing is published
-                // for this tile until then, so the tiles after it wait
+                // the warps start the exact evaluation at once (windows, pass A, transfer functions) while the exact prefix
+                // is taken; the mark-by-mark pass then runs with the backlog that really enters.  Nothing is published for
+                // this tile until then, so the tiles after it wait
 #ifdef LATOK_PROFILE
                 const long long _s0 = clock64();
 #endif
+                order_exact(0, false);
                 pre = lookback(tile, p, lane);
 #ifdef LATOK_PROFILE
                 const long long _s1 = clock64();
 #endif
-                order_exact(pre.x); gather();
+                give_backlog(pre.x); gather();
 #ifdef LATOK_PROFILE
                 if (lane == 0) { atomicAdd(&p.result->prof[9], (unsigned long long)(_s1 - _s0)); atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
 #endif
@@ -206,7 +230,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
 #ifdef LATOK_PROFILE
                     const long long _s1 = clock64();
 #endif
-                    order_exact(pre.x); gather();
+                    order_exact(pre.x, true); gather();
 #ifdef LATOK_PROFILE
                     if (lane == 0) { atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
 #endif
@@ -342,8 +366,14 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             st_vs32(reinterpret_cast<int *>(&ctl.xfgen[cw]), (int)round);
         }
     };
-    auto backlog_in = [&](int x_tile, unsigned round) -> int {
-        int fu = 0, fv = NEG;
+    auto backlog_in = [&](int slot, unsigned round) -> int {
+        int fu = 0, fv = NEG, x_tile = 0;
+        if (lane == 0) {                 // the backlog that enters the tile (handed down once the look-back has it)
+            unsigned spins = 0;
+            while ((unsigned)ld_vs32(&ctl.xr[slot]) != round) { if (++spins > (1u << 27)) { atomicOr(&p.result->error, 1u); break; } }
+            x_tile = ld_vs32(&ctl.slot[slot].x_in);
+        }
+        x_tile = __shfl_sync(FULL, x_tile, 0);
         if (lane < cw) {
             unsigned spins = 0;
             while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xfgen[lane])) != round) { if (++spins > (1u << 26)) { atomicOr(&p.result->error, 1u); break; } }
@@ -359,9 +389,13 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0; bool a_irregular = false;
 
     // ================================================================================================= analysis
-    auto analyze = [&](const long long r, const int buf, const bool exact, const unsigned round, const int x_tile) {
+    auto analyze = [&](const long long r, const int buf, const bool exact, const unsigned round) {
         const long long w0 = r * (long long)RANGE;
         const bool have = r < p.nranges, last_range = r == p.nranges - 1;
+#ifdef LATOK_PROFX
+        long long _px = clock64();
+        if (exact && lane == 0) atomicAdd(&p.result->prof[7], 1ull);
+#endif
         uint8_t *X = Xof(buf);
         uint32_t *tempS = tempof(buf);
         int c_lo = 0, c_hi = CINF, n_own = 0, ntok_range = 0, lft = -1, v_out = 0, far = 0;
@@ -378,7 +412,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         if (!have) {
             if (exact) {      // pass the backlog on
                 publish_fn(fn_id(), round);
-                v_out = backlog_in(x_tile, round);
+                v_out = backlog_in(buf, round);
             }
             c_hi = 0;
             finish();
@@ -639,6 +673,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             Fp = Fc; leadp = leadc; np = nc; c0p = c0c;
         }
         PROF5(1);
+        PROFX(0);
         if (c_hi == CINF) c_hi = crun;           // (defensive; every range sets it)
         n_own = c_hi - c_lo;
         if (n_own < 0) n_own = 0;
@@ -689,8 +724,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 }
                 publish_fn(rf, round);
             }
+            PROFX(1);
             // B2: the backlog that really enters, then mark by mark
-            int x = backlog_in(x_tile, round);
+            int x = backlog_in(buf, round);
+            PROFX(2);
             int v_nom = 0;
 #pragma unroll 1
             for (int js = 0; js < RS; ++js) {
@@ -706,6 +743,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 T_at(js, I_H) = HOT;
             }
             v_out = closed ? x : v_nom;
+            PROFX(3);
             // the chunk still open at the end of the trusted halo: hot if a backlog is pending, else look ahead for a mark
             if (!closed) {
                 const uint32_t pk = T_at(RS - 1, I_K);
@@ -731,6 +769,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             }
         }
         PROF5(2);
+        PROFX(4);
         // ---------------------------------------------------------------- pass C: blanked chunks, values, tokens
         {
             uint32_t bin_step = (uint32_t)far;
@@ -820,6 +859,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         }
         finish();
         PROF5(3);
+        PROFX(5);
     };
 
     // ================================================================================================= output
@@ -1246,8 +1286,14 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             nb_sync(BAR_PRE + s, NTH);
             if (ctl.slot[s].mode == 0) break;
             ++round;
+#ifdef LATOK_PROFX
+            const long long _pl = clock64();
+#endif
             if (r < p.nranges) plain_load(r, s);
-            analyze(r, s, true, round, ctl.slot[s].x_in);
+#ifdef LATOK_PROFX
+            if (lane == 0) atomicAdd(&p.result->prof[6], (unsigned long long)(clock64() - _pl));
+#endif
+            analyze(r, s, true, round);
             exact_done = true;
             post(s);
         }
@@ -1285,7 +1331,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             if (s == 0 ? pending[0] : pending[1]) wait_window(s, phase_bits);
             __syncwarp();
             PROF5(0);
-            analyze((long long)tile_cur * NW + cw, s, false, 0u, 0);
+            analyze((long long)tile_cur * NW + cw, s, false, 0u);
             post(s);
         } else {
             nb_arrive(BAR_AGG + s, NTH);                 // tells the service warp that the tickets have run out

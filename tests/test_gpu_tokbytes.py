@@ -76,3 +76,28 @@ def test_needs_spans(engine):
     engine.submit(buf, off, SPLITS)
     with pytest.raises(RuntimeError):
         engine.token_bytes()
+
+
+def test_timing_cli_outfile_matches_reference_format(tmp_path):
+    """tools/time_tokenizer.py (counterpart of scripts/timing/time_tokenizer.py:65-123): csv.gz in, one line of
+    tab-separated tokens per row out."""
+    import csv
+    import gzip
+    import subprocess
+    import sys
+    texts = [t for t in corpus.FIXTURES + corpus.fuzz_strings(21, 300, 120) if "\x00" not in t]
+    texts = [t for t in texts if not any(0xD800 <= ord(c) <= 0xDFFF for c in t)] + ["", "   "]
+    src = tmp_path / "in.csv.gz"
+    with gzip.open(src, "wt", encoding="utf-8", newline="") as f:
+        w = csv.writer(f)
+        for i, t in enumerate(texts):
+            w.writerow([i, json.dumps(t)])
+    out = tmp_path / "out.tsv"
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "tools" / "time_tokenizer.py"), str(src), "--outfile", str(out),
+                        "--batch", "64"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = b"".join("\t".join(oracle.tokens(t.strip()) if t.strip() else []).encode("utf-8") + b"\n" for t in texts)
+    assert out.read_bytes() == want
+    stats = json.loads(r.stdout.strip().splitlines()[-1])
+    assert stats["lines"] == len(texts)

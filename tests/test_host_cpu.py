@@ -189,3 +189,52 @@ def test_bit_plane_primitives_selftest(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "bits selftest ok" in out.stdout
+
+
+def test_timing_cli_tsv_assembly():
+    """tools/time_tokenizer.py builds the --outfile rows ('\\t'.join(tokens) per input row,
+    scripts/timing/time_tokenizer.py:105-107) from token byte ranges with NumPy gathers only."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    from time_tokenizer import pack, tsv_bytes
+    rows = [["ab", "cd"], [], [], ["e"], ["日本", "x"], []]
+    texts = [" ".join(r) for r in rows]
+    buf, off = pack([t.encode() for t in texts])
+    spans, toff = [], [0]
+    for t, o in zip(texts, off[:-1]):
+        b = t.encode()
+        p = 0
+        for tok in t.split():
+            p = b.index(tok.encode(), p)
+            spans.append((o + p, o + p + len(tok.encode())))
+            p += len(tok.encode())
+        toff.append(len(spans))
+    got = tsv_bytes(buf, np.array(spans, dtype=np.int64).reshape(-1, 2), np.array(toff, dtype=np.int64))
+    assert got == "".join("\t".join(r) + "\n" for r in rows).encode()
+    assert tsv_bytes(buf[:0], np.zeros((0, 2), np.int64), np.array([0, 0, 0], np.int64)) == b"\n\n"
+
+
+def test_table_regeneration_rules_reproduce_ucd11():
+    """tools/regen_classes.py applies the reference's flag rules (makeunicodedata.py:158-200,249-258) to the UCD of
+    the running Python.  Wherever UCD 11 gave a code point features, the rules must give the same ones (a handful of
+    code points changed properties in later UCD versions); the rest of the difference is newly assigned code points.
+    The ranges file it writes reads back to the same classes."""
+    import subprocess
+    import sys
+    import tempfile
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root / "tools"))
+    import regen_classes as rc
+    old = rc.read_ranges(rc.UCD11)
+    feat = [rc.base_features(cp) for cp in range(0x110000)]
+    assert feat[:128] == old[:128]
+    redefined = [cp for cp in range(0x110000) if old[cp] != 0 and feat[cp] != old[cp]]
+    assert len(redefined) <= 8, [hex(c) for c in redefined[:20]]
+    assert len(set(feat)) <= 17
+    spaces = [cp for cp in range(0x110000) if feat[cp] & 0x20]
+    assert spaces == [cp for cp in range(0x110000) if chr(cp).isspace()]          # SURVEY Q9
+    with tempfile.TemporaryDirectory() as d:
+        out = Path(d) / "ucd_new.txt"
+        subprocess.run([sys.executable, str(root / "tools" / "regen_classes.py"), "--out", str(out)], check=True)
+        assert rc.read_ranges(out) == feat
