@@ -183,24 +183,35 @@ __global__ void __launch_bounds__(256) token_bytes_kernel(const TokBytesParams p
         }
         if (!live) continue;
         const long long o0 = p.offsets[s], o1 = p.offsets[s + 1], c0 = p.char_off[s], c1 = p.char_off[s + 1];
-        const bool ascii = (o1 - o0) == (c1 - c0);
-        const long long w_lo = o0 / TB_WORD, w_hi = (o1 - 1) / TB_WORD;
-        // byte position of the string's character number idx (idx == length: the end of the string); `hint`: a word
-        // that is known to begin at or before the character (-1: none)
-        long long word_of_last = -1;
-        const float ratio = __fdividef((float)(o1 - o0), (float)(c1 - c0));
-        auto byte_of = [&](long long idx, long long hint) -> long long {
-            if (ascii) return o0 + idx;
-            if (idx >= c1 - c0) return o1;
-            const unsigned long long g = (unsigned long long)(c0 + idx);
-            long long lo = w_lo, hi = w_hi, step = 1;
+        const unsigned len_b = (unsigned)(o1 - o0), len_c = (unsigned)(c1 - c0);
+        const bool ascii = len_b == len_c;
+        // Everything below is relative to the string and fits 32 bits (spans are int32): word wr = the 32-byte word
+        // w_lo + wr of the text, wp(wr) = characters of THE STRING in front of that word (<= 0 for wr = 0 when the string
+        // begins inside the word), taken modulo 2^32 from the 64-bit prefix
+        const long long w_lo = o0 / TB_WORD;
+        const int nw = (int)((o1 - 1) / TB_WORD - w_lo);                  // the string's last word
+        const unsigned c0lo = (unsigned)c0, skew = (unsigned)(o0 - w_lo * TB_WORD);
+        const unsigned *gp_lo = reinterpret_cast<const unsigned *>(p.group_pref);      // low halves (little endian)
+        auto wp = [&](int wr) -> int {
+            const long long w = w_lo + wr;
+            return (int)(gp_lo[2 * (w / TB_GROUP)] + p.word_local[w] - c0lo);
+        };
+        // byte position (relative to the string) of its character number idx; idx == length: the end of the string;
+        // `hint`: a word known to begin at or before the character (-1: none)
+        int word_of_last = -1;
+        const float ratio = __fdividef((float)len_b, (float)len_c);
+        auto byte_of = [&](unsigned idx, int hint) -> unsigned {
+            if (ascii) return idx;
+            if (idx >= len_c) return len_b;
+            const int g = (int)idx;
+            int lo = 0, hi = nw, step = 1;
             if (hint >= 0) lo = hint;
             else {
-                long long probe = (o0 + (long long)((float)idx * ratio)) / TB_WORD;
-                probe = probe < lo ? lo : (probe > hi ? hi : probe);
+                int probe = (int)((skew + (unsigned)((float)idx * ratio)) / TB_WORD);
+                probe = probe > hi ? hi : probe;
                 if (wp(probe) <= g) lo = probe;
                 else {
-                    long long h = probe;                                  // wp(h) > g
+                    int h = probe;                                        // wp(h) > g
                     while (h - step > lo && wp(h - step) > g) { h -= step; step <<= 1; }
                     lo = h - step > lo ? h - step : lo;
                     hi = h - 1; step = hi - lo + 1;                       // (no galloping up below: bisect [lo, hi])
@@ -211,14 +222,15 @@ __global__ void __launch_bounds__(256) token_bytes_kernel(const TokBytesParams p
                 if (lo + step - 1 < hi) hi = lo + step - 1;
             }
             while (lo < hi) {
-                const long long mid = (lo + hi + 1) >> 1;
+                const int mid = (lo + hi + 1) >> 1;
                 if (wp(mid) <= g) lo = mid; else hi = mid - 1;
             }
             word_of_last = lo;
-            return lo * TB_WORD + select32(lead_mask32(p.in, lo * TB_WORD, p.n_bytes), (unsigned)(g - wp(lo)));
+            const int pos = select32(lead_mask32(p.in, (w_lo + lo) * TB_WORD, p.n_bytes), (unsigned)(g - wp(lo)));
+            return (unsigned)lo * TB_WORD + (unsigned)pos - skew;
         };
-        long long bs = byte_of(sp_cur.x, -1);
-        const long long be = byte_of(sp_cur.y, word_of_last);
+        long long bs = o0 + byte_of((unsigned)sp_cur.x, -1);
+        const long long be = o0 + byte_of((unsigned)sp_cur.y, word_of_last);
         // strip(): only the span's first character can be whitespace
         if (bs < be) {
             const uint8_t *q = p.in + bs;

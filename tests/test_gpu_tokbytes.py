@@ -101,3 +101,29 @@ def test_timing_cli_outfile_matches_reference_format(tmp_path):
     assert out.read_bytes() == want
     stats = json.loads(r.stdout.strip().splitlines()[-1])
     assert stats["lines"] == len(texts)
+
+
+def test_device_resident_text_and_device_output(engine):
+    """Text submitted from device memory, byte ranges written to a caller's device array (on_device = 1)."""
+    import ctypes as C
+    import torch
+    from latok_b200 import _lib
+    from latok_b200.engine import SPANS, pack_strings
+    texts = [t for t in corpus.fuzz_strings(31, 800, 150, "mixed") if t]
+    buf, off = pack_strings(texts)
+    d_buf = torch.from_numpy(buf.copy()).cuda()
+    d_off = torch.from_numpy(off.copy()).cuda()
+    engine.submit_device(d_buf.data_ptr(), d_off.data_ptr(), len(texts), len(buf), SPANS)
+    r = engine.fetch()
+    d_out = torch.empty((r.n_tokens, 2), dtype=torch.int64, device="cuda")
+    _lib.check(_lib.load().latok_b200_fetch_token_bytes(engine._h, d_out.data_ptr(), 1))
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    assert np.array_equal(got, engine.token_bytes())
+    mv = memoryview(buf)
+    for i in (0, 1, len(texts) // 2, len(texts) - 1):
+        toks = [bytes(mv[b:e]).decode("utf-8", "surrogatepass") for b, e in got[r.tok_offsets[i]:r.tok_offsets[i + 1]]]
+        assert toks == oracle.tokens(texts[i])
+    # a misaligned device pointer is rejected, not written through
+    with pytest.raises(ValueError):
+        _lib.check(_lib.load().latok_b200_fetch_token_bytes(engine._h, d_out.data_ptr() + 8, 1))
