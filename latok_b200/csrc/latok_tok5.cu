@@ -56,6 +56,7 @@ struct Ctl {
     int tile_id[2], tk_cnt[2], tk_flag[2];
     int xr[2];                           // exact evaluation: the round for which slot[].x_in (the backlog entering the tile) is valid
     int pad0[2];
+    int patch_x[NW];                     // mode 2: backlog with which a range repeats its (regular) analysis, -1: not this range
     Slot slot[2];
     WAgg wagg[2][NW];
     int xfu[NW], xfv[NW];                // exact evaluation: backlog transfer function of every range of the tile
@@ -160,6 +161,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         for (int k = 0;; ++k) {
             const int s = k & 1;
             int n = 0, ntok = 0, lft_rel = -1, v = 0; bool irregular = false;
+            int v_range = 0;             // lane i: backlog that range i hands to the next one
+            int x_used = 0;              // lane i: backlog with which range i has been analysed
             auto gather = [&]() {
                 nb_sync(BAR_AGG + s, NTH);
                 const WAgg a = ctl.wagg[s][lane < NW ? lane : 0];
@@ -174,7 +177,27 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 const int lv = __shfl_sync(FULL, pn - mn + a.lft, src);
                 lft_rel = hl ? lv : -1;
                 v = __shfl_sync(FULL, a.v, NW - 1);
+                v_range = lane < NW ? a.v : 0;
                 irregular = __any_sync(FULL, lane < NW && (a.flags & 1));
+            };
+            // Regular tile (every range begins and ends at a chunk closer): a range that ends in a chunk with several marks
+            // hands a backlog to the next range, which then repeats its ordinary analysis with that backlog entering
+            // (mode 2; nothing else of the tile is touched).  Repeats until every range has seen the backlog its
+            // predecessor really leaves; `x_tile` = backlog entering the tile.
+            auto settle = [&](int x_tile) {
+                for (;;) {
+                    int want = __shfl_up_sync(FULL, v_range, 1);
+                    if (lane == 0) want = x_tile;
+                    const bool need = lane < NW && want != x_used;
+                    if (!__any_sync(FULL, need)) break;
+                    if (lane < NW) st_vs32(&ctl.patch_x[lane], need ? want : -1);
+                    if (need) x_used = want;
+                    if (lane == 0) { ctl.slot[s].mode = 2; atomicAdd(&p.result->prof[15], 1ull); }
+                    __threadfence_block();
+                    __syncwarp();
+                    nb_arrive(BAR_PRE + s, NTH);
+                    gather();
+                }
             };
             // the compute warps are told to run the exact evaluation; the backlog that enters the tile may follow later
             // (give_backlog): reload, pass A and the ranges' transfer functions do not need it
@@ -219,6 +242,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
 #endif
                 if (lane == 0) atomicAdd(&p.result->prof[15], 1ull);
             } else {
+                settle(0);
                 const unsigned ylf = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
                 if (lane == 0) {
                     uint4 r;
@@ -230,7 +254,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
 #ifdef LATOK_PROFILE
                     const long long _s1 = clock64();
 #endif
-                    order_exact(pre.x, true); gather();
+                    settle(pre.x);
 #ifdef LATOK_PROFILE
                     if (lane == 0) { atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
 #endif
@@ -389,7 +413,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0; bool a_irregular = false;
 
     // ================================================================================================= analysis
-    auto analyze = [&](const long long r, const int buf, const bool exact, const unsigned round) {
+    auto analyze = [&](const long long r, const int buf, const bool exact, const unsigned round, const int x_init) {
         const long long w0 = r * (long long)RANGE;
         const bool have = r < p.nranges, last_range = r == p.nranges - 1;
 #ifdef LATOK_PROFX
@@ -454,7 +478,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
 #pragma unroll
         for (int f = 0; f < NBASE; ++f) Pp[f] = 0;
         int crun = 0;                    // characters of the range so far
-        int xb = 0;                      // block-mask backlog entering the next step (fast evaluation: 0 or 1 mark pending)
+        int xb = x_init;                 // block-mask backlog entering the next step (regular evaluation; 0 almost always)
 
 #pragma unroll 1
         for (int j = 0; j <= RS; ++j) {
@@ -678,13 +702,15 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         n_own = c_hi - c_lo;
         if (n_own < 0) n_own = 0;
         if (!exact) {
-            // not covered here: a range that does not begin / end at a chunk closer, or one that hands a backlog on
-            irregular = !lo_found || !closed || xb != 0;
+            // not covered here: a range that does not begin / end at a chunk closer.  A backlog left by the range's last
+            // chunk (several marks) is handed to the next range by the service warp (settle)
+            irregular = !lo_found || !closed;
+            v_out = xb;
+            if (lane == 0 && xb != 0) atomicAdd(&p.result->prof[14], 1ull);      // (statistics)
             if (irregular) {                       // the tile is analysed again by the exact evaluation
                 if (lane == 0) {                   // (statistics: why)
                     if (!lo_found) atomicAdd(&p.result->prof[12], 1ull);
                     if (!closed) atomicAdd(&p.result->prof[13], 1ull);
-                    if (xb != 0) atomicAdd(&p.result->prof[14], 1ull);
                 }
                 finish(); return;
             }
@@ -1284,8 +1310,16 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         bool exact_done = false;
         for (;;) {
             nb_sync(BAR_PRE + s, NTH);
-            if (ctl.slot[s].mode == 0) break;
-            ++round;
+            const int mode = ctl.slot[s].mode;
+            if (mode == 0) break;
+            // mode 1: the exact evaluation of the whole tile.  mode 2: a backlog enters this range after all -- its ordinary
+            // analysis once more, with it (the other ranges of the tile just answer; what they posted stands).
+            // (ONE call site for both: a second inlined copy of the analysis costs the regular path instruction-cache misses)
+            int px = 0;
+            if (mode == 2) {
+                px = ld_vs32(&ctl.patch_x[cw]);
+                if (px < 0 || r >= p.nranges) { nb_arrive(BAR_AGG + s, NTH); continue; }
+            } else ++round;
 #ifdef LATOK_PROFX
             const long long _pl = clock64();
 #endif
@@ -1293,8 +1327,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
 #ifdef LATOK_PROFX
             if (lane == 0) atomicAdd(&p.result->prof[6], (unsigned long long)(clock64() - _pl));
 #endif
-            analyze(r, s, true, round);
-            exact_done = true;
+            analyze(r, s, mode == 1, round, px);
+            if (mode == 1) exact_done = true;
             post(s);
         }
         PROF5(4);
@@ -1331,7 +1365,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             if (s == 0 ? pending[0] : pending[1]) wait_window(s, phase_bits);
             __syncwarp();
             PROF5(0);
-            analyze((long long)tile_cur * NW + cw, s, false, 0u);
+            analyze((long long)tile_cur * NW + cw, s, false, 0u, 0);
             post(s);
         } else {
             nb_arrive(BAR_AGG + s, NTH);                 // tells the service warp that the tickets have run out
