@@ -238,3 +238,26 @@ def test_table_regeneration_rules_reproduce_ucd11():
         out = Path(d) / "ucd_new.txt"
         subprocess.run([sys.executable, str(root / "tools" / "regen_classes.py"), "--out", str(out)], check=True)
         assert rc.read_ranges(out) == feat
+
+
+def test_bench_config5_batch_shards_cover_the_batch():
+    """bench.py --workload chars1b: every rank builds the same batch and keeps its byte-balanced range of whole
+    strings; the ranges tile the batch and are balanced to within one string."""
+    import importlib.util
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("bench_mod", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from latok_b200.sharding import shard_ranges, slice_shard
+    buf, off = bench.make_batch("chars1b", 6000, 0)
+    buf2, off2 = bench.make_batch("chars1b", 6000, 0)
+    assert np.array_equal(buf, buf2) and np.array_equal(off, off2)            # same on every rank
+    assert off[0] == 0 and off[-1] == len(buf) and np.all(np.diff(off) > 0) and len(off) == 6001
+    for world in (1, 2, 4, 8):
+        ranges = shard_ranges(off, world)
+        assert ranges[0][0] == 0 and ranges[-1][1] == 6000
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        parts = [slice_shard(buf, off, s0, s1) for s0, s1 in ranges]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), buf)
+        sizes = [len(p[0]) for p in parts]
+        assert max(sizes) - min(sizes) <= 2 * int(np.diff(off).max())
