@@ -126,6 +126,20 @@ LATOK_B200_API int latok_b200_launch_count(latok_b200_engine *e, int64_t *launch
  * scan ahead beyond their halo to close a whitespace chunk */
 LATOK_B200_API int latok_b200_last_stats(latok_b200_engine *e, float *tokenize_kernel_ms, int64_t *lookahead_walks);
 
+/* ---- ingest: csv / csv.gz rows -> packed batch (host code; counterpart of the per-row loop of
+ *      scripts/timing/time_tokenizer.py:25-40, `text = json.loads(row[column]).strip()`) ------------- */
+typedef struct latok_b200_reader latok_b200_reader;
+/* `path` may be gzip-compressed; `column` is the csv column that holds the JSON-encoded text (the reference uses 1). */
+LATOK_B200_API int latok_b200_reader_open(const char *path, int column, latok_b200_reader **out);
+/* Packs up to max_rows further rows: their stripped UTF-8 is appended to utf8 (capacity utf8_cap bytes; pinned memory
+ * from latok_b200_host_alloc goes to latok_b200_submit without another copy) and offsets[0..*n_rows] receives the
+ * running byte offsets (offsets needs max_rows + 1 entries).  Stops early when the next row would not fit;
+ * *n_rows == 0 means end of file.  A row without that column, or whose column is not a JSON string, is an error
+ * (LATOK_B200_EINVAL), as it is in the reference's loop. */
+LATOK_B200_API int latok_b200_reader_next(latok_b200_reader *r, int64_t max_rows, uint8_t *utf8, int64_t utf8_cap,
+                           int64_t *offsets, int64_t *n_rows);
+LATOK_B200_API int latok_b200_reader_close(latok_b200_reader *r);
+
 /* ---- pinned host memory for callers that want zero-copy staging --------------------------- */
 LATOK_B200_API int latok_b200_host_alloc(void **ptr, size_t bytes);
 LATOK_B200_API int latok_b200_host_free(void *ptr);

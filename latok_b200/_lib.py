@@ -54,6 +54,9 @@ def load():
         "latok_b200_timer_end": (C.c_int, [vp, P(C.c_float)]),
         "latok_b200_launch_count": (C.c_int, [vp, P(i64)]),
         "latok_b200_last_stats": (C.c_int, [vp, P(C.c_float), P(i64)]),
+        "latok_b200_reader_open": (C.c_int, [C.c_char_p, i32, P(vp)]),
+        "latok_b200_reader_next": (C.c_int, [vp, i64, vp, i64, vp, P(i64)]),
+        "latok_b200_reader_close": (C.c_int, [vp]),
         "latok_b200_host_alloc": (C.c_int, [P(vp), sz]),
         "latok_b200_host_free": (C.c_int, [vp]),
         "latok_b200_gen_parse_matrix": (C.c_int, [vp, vp, i64, P(i64), vp]),

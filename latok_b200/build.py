@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "liblatok_b200.so"
-SOURCES = [CSRC / "latok_kernels.cu", CSRC / "latok_tok5.cu", CSRC / "latok_tokbytes.cu", CSRC / "latok_capi.cu"]
+SOURCES = [CSRC / "latok_kernels.cu", CSRC / "latok_tok5.cu", CSRC / "latok_tokbytes.cu", CSRC / "latok_capi.cu", CSRC / "latok_reader.cpp"]
 HEADERS = [CSRC / "latok_internal.h", CSRC / "latok_bits.h", CSRC / "latok_device.cuh", ROOT / "include" / "latok_b200.h"]
 GEN = CSRC / "_gen" / "latok_tables.h"
 RANGES = PKG / "data" / "ucd11_latok_classes.txt"
@@ -56,7 +56,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         cmd += os.environ["LATOK_DEFS"].split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [str(s) for s in SOURCES] + ["-o", str(LIB)]
+    cmd += [str(s) for s in SOURCES] + ["-lz", "-o", str(LIB)]        # zlib: the csv.gz reader (latok_reader.cpp)
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -154,6 +154,16 @@ struct latok_b200_engine {
     float last_kernel_ms = 0.f;
 };
 
+// for the other translation units of the library (latok_reader.cpp)
+extern "C" int latok_b200_set_error_(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
 static int set_device(latok_b200_engine *e)
 {
     CU(cudaSetDevice(e->device));

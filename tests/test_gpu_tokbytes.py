@@ -92,15 +92,16 @@ def test_timing_cli_outfile_matches_reference_format(tmp_path):
         w = csv.writer(f)
         for i, t in enumerate(texts):
             w.writerow([i, json.dumps(t)])
-    out = tmp_path / "out.tsv"
     root = Path(__file__).resolve().parent.parent
-    r = subprocess.run([sys.executable, str(root / "tools" / "time_tokenizer.py"), str(src), "--outfile", str(out),
-                        "--batch", "64"], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
     want = b"".join("\t".join(oracle.tokens(t.strip()) if t.strip() else []).encode("utf-8") + b"\n" for t in texts)
-    assert out.read_bytes() == want
-    stats = json.loads(r.stdout.strip().splitlines()[-1])
-    assert stats["lines"] == len(texts)
+    for reader in ("native", "python"):        # latok_reader.cpp into pinned buffers / the csv + json modules
+        out = tmp_path / f"out_{reader}.tsv"
+        r = subprocess.run([sys.executable, str(root / "tools" / "time_tokenizer.py"), str(src), "--outfile", str(out),
+                            "--batch", "64", "--batch-bytes", "65536", "--reader", reader], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert out.read_bytes() == want, reader
+        stats = json.loads(r.stdout.strip().splitlines()[-1])
+        assert stats["lines"] == len(texts) and stats["reader"] == reader
 
 
 def test_device_resident_text_and_device_output(engine):

@@ -261,3 +261,41 @@ def test_bench_config5_batch_shards_cover_the_batch():
         assert np.array_equal(np.concatenate([p[0] for p in parts]), buf)
         sizes = [len(p[0]) for p in parts]
         assert max(sizes) - min(sizes) <= 2 * int(np.diff(off).max())
+
+
+def test_native_csv_reader_matches_python_csv_json(tmp_path):
+    """latok_b200_reader_* (host code, no GPU): the packed batches equal `json.loads(row[1]).strip()` per csv row
+    (scripts/timing/time_tokenizer.py:25-40) -- quoting, escapes, surrogate pairs, every whitespace character at both
+    ends, gzip, rows that do not fit the buffer, and the reference's failure cases."""
+    import csv
+    import gzip
+    import json
+    from latok_b200.reader import CsvReader
+    spaces = "".join(chr(c) for c in range(0x110000) if chr(c).isspace())
+    texts = list(corpus.FIXTURES) + corpus.fuzz_strings(41, 400, 150, "mixed")
+    texts += [spaces + "x" + spaces, spaces, "", 'a "quoted", value', "comma,inside", "tab\tinside and \\ backslash",
+              "\U0001F600 astral \ud83d lone", "line\nbreak\r\nin text", "\x00nul\x1f"]
+    for name, ensure_ascii, opener in (("a.csv", True, open), ("b.csv.gz", False, gzip.open)):
+        path = tmp_path / name
+        with opener(path, "wt", encoding="utf-8", errors="surrogatepass", newline="") as f:
+            w = csv.writer(f)
+            for i, t in enumerate(texts):
+                w.writerow([i, json.dumps(t, ensure_ascii=ensure_ascii), "third, column"])
+        # (json.loads, not the original text: it joins an escaped high + low surrogate pair into one code point)
+        want = [json.loads(json.dumps(t, ensure_ascii=ensure_ascii)).strip().encode("utf-8", "surrogatepass") for t in texts]
+        for rows, nbytes in ((1000, 1 << 20), (7, 1 << 20), (1000, 700)):
+            got = []
+            with CsvReader(str(path), batch_rows=rows, batch_bytes=nbytes) as r:
+                for buf, off in r:
+                    assert off[0] == 0 and off[-1] == len(buf)
+                    got += [bytes(buf[off[i]:off[i + 1]]) for i in range(len(off) - 1)]
+            assert got == want, (name, rows, nbytes)
+    # failure cases of the reference's loop: no column 1 (IndexError there), not a JSON string (AttributeError there)
+    for content in ("0\n", '0,"123"\n', '0,"{""a"": 1}"\n', '0,"""unterminated"\n'):
+        bad = tmp_path / "bad.csv"
+        bad.write_text(content)
+        with pytest.raises(ValueError):
+            with CsvReader(str(bad)) as r:
+                list(r)
+    with pytest.raises(ValueError):
+        CsvReader(str(tmp_path / "missing.csv"))

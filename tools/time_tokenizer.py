@@ -78,7 +78,11 @@ def main():
     ap.add_argument("--mincount", type=int, default=100000, help="rows between progress lines")
     ap.add_argument("--outfile", help="write the tokens of every row, tab-separated, one row per line")
     ap.add_argument("--batch", type=int, default=200_000, help="rows per GPU batch")
+    ap.add_argument("--batch-bytes", type=int, default=64 << 20, help="native reader: UTF-8 bytes per GPU batch at most")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--reader", choices=["native", "python"], default="native",
+                    help="native: rows parsed, JSON-decoded, stripped and packed by liblatok_b200 (latok_reader.cpp) into "
+                         "pinned buffers; python: csv + json modules")
     args = ap.parse_args()
     print(f"{datetime.now()}: {args}", file=sys.stderr)
     from latok_b200.engine import Engine, FEATS, MATRIX, SPANS, SPLITS
@@ -86,9 +90,19 @@ def main():
     what = SPLITS if split else MATRIX if matrix else (SPANS | FEATS) if args.features else SPANS
 
     q: "queue.Queue" = queue.Queue(maxsize=2)
+    done = threading.Event()
 
     def reader():
         try:
+            if args.reader == "native":
+                from latok_b200.reader import CsvReader
+                # 4 buffer sets: one in the GPU call, two queued, one being filled
+                with CsvReader(args.infile, args.batch, args.batch_bytes, pinned=True, n_buffers=4) as rd:
+                    for item in rd:
+                        q.put(item)
+                    q.put(None)
+                    done.wait()              # the pinned buffers must outlive the last GPU call
+                return
             for item in read_batches(args.infile, args.batch):
                 q.put(item)
             q.put(None)
@@ -126,13 +140,15 @@ def main():
                 dt = time.perf_counter() - t_start
                 print(f"{datetime.now()}: {rows} lines, {rows / dt:.0f} lines/s, {n_bytes / dt / 1e6:.1f} MB/s", file=sys.stderr)
                 next_report += args.mincount
+    done.set()
     if out is not None:
         out.close()
     dt = time.perf_counter() - t_start
     print(f"{datetime.now()}: ...tokenized {rows} lines")
     print(json.dumps({"lines": rows, "bytes": n_bytes, "tokens": n_tokens, "seconds": dt, "lines_per_s": rows / dt,
                       "MB_per_s": n_bytes / dt / 1e6, "gpu_call_seconds": gpu_s, "write_seconds": write_s,
-                      "mode": "split" if split else "matrix" if matrix else "features" if args.features else "tokenize"}))
+                      "mode": "split" if split else "matrix" if matrix else "features" if args.features else "tokenize",
+                      "reader": args.reader}))
     return 0
 
 
