@@ -20,6 +20,9 @@
 //   -> the service warp sums the ranges of the tile, publishes the aggregate, looks back, hands the prefix down
 //   pass D  forward: split bytes and (start,end) pairs staged per step in shared memory and written with
 //           aligned 16-byte stores; CSR offsets by one lane per string.
+// Rare paths: a backlog left by a range's last chunk (several marks) is handed to the next range, which repeats its
+// ordinary analysis with it (mode 2, settle()); a range that does not begin / end at a chunk closer (space-free run
+// longer than the search windows) sends its tile through the exact evaluation (mode 1, pass B + look-ahead walk).
 // The warps run one tile ahead of the look-back: analysis of tile k+1, then pass D of tile k, whose state waits in
 // place of its input bytes (two window buffers per warp).  Tickets are taken by the first warp that is ready for the
 // next tile, so ticket order follows start order and predecessors publish first.

@@ -272,3 +272,29 @@ def test_back_to_back_submits_alternate_index_sets(engine):
         assert r.n_chars == ref["n_chars"] and r.n_tokens == ref["n_tokens"]
         assert np.array_equal(r.splits, ref["splits"]) and np.array_equal(r.spans, ref["spans"])
         assert np.array_equal(r.char_offsets, ref["char_offsets"]) and np.array_equal(r.tok_offsets, ref["tok_offsets"])
+
+
+def test_backlog_handoff_between_ranges(engine):
+    """A chunk with several marks that ends right at a range end hands its backlog to the next range (the service warp's
+    settle(): the next range repeats its ordinary analysis with the backlog entering): swept over the range end, with
+    hand-offs in consecutive ranges (cascade), across a tile boundary, from a tile's last range into the next tile, and
+    with backlogs larger than one."""
+    filler = "lorem ipsum dolor sit amet consectetur "
+    marks = ["aa@bb,cc@dd xx", "aa@bb,cc@dd,ee@ff,gg@hh xx yy zz", "http://a.b/c,x@y,#t d@e.f,g@h uu vv ww",
+             "a@b,c@d,e@f,g@h,i@j,k@l,m@n one two three four five six seven"]
+    texts = []
+    for shift in range(0, 64, 3):
+        for m in marks:
+            parts, pos = [], 0
+            for k in range(1, 21):                      # one multi-mark chunk near the end of each of 20 ranges (2 tiles + 2)
+                target = 3968 * k - 20 + shift - len(m) // 2
+                pad = max(target - pos, 1)
+                fill = (filler * (pad // len(filler) + 1))[:pad - 1] + " "
+                parts += [fill, m + " "]
+                pos += len(fill) + len(m) + 1
+            texts.append("".join(parts))
+    check_batch(engine, texts[:40], ALL, label="hand-off, all outputs")
+    check_batch(engine, texts, 3, label="hand-off")
+    # the same chunks with no space after them for a long while: the backlog is carried through several ranges
+    long_tail = ["pre fix " + m + " " + ("word,word;word/" * 1200) + " end tail a b c" for m in marks]
+    check_batch(engine, long_tail, 7, label="hand-off into a space-free run")
