@@ -56,11 +56,14 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         cmd += os.environ["LATOK_DEFS"].split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [str(s) for s in SOURCES] + ["-lz", "-o", str(LIB)]        # zlib: the csv.gz reader (latok_reader.cpp)
+    # LATOK_B200_LIB_OUT: build somewhere else (e.g. a library for a newer UCD: LATOK_CLASSES / LATOK_LOW_LIMIT are read
+    # by tools/gen_tables.py; the next default build regenerates the UCD-11 tables)
+    out = Path(os.environ.get("LATOK_B200_LIB_OUT") or LIB)
+    cmd += [str(s) for s in SOURCES] + ["-lz", "-o", str(out)]        # zlib: the csv.gz reader (latok_reader.cpp)
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

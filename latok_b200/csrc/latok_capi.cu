@@ -194,7 +194,7 @@ static int build_table(latok_b200_engine *e)
     tl.lutv = take(256 * 4);
     tl.ascii_feat = take(128 * 2);
     tl.class_feat = take(16 * 2);
-    tl.stage1 = take(LATOK_TBL_STAGE1_LEN);
+    tl.stage1 = take(LATOK_TBL_STAGE1_LEN * (int)sizeof(latok_stage1_t));
     tl.stage2 = take(LATOK_TBL_STAGE2_LEN);
     tl.total = o;
     tl.stage1_len = LATOK_TBL_STAGE1_LEN;

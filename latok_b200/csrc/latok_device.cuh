@@ -84,7 +84,7 @@ __device__ __forceinline__ void st_volatile_u32(unsigned *p, unsigned v)
 struct Tables {
     const uint16_t *ascii_feat;
     const uint16_t *class_feat;
-    const uint8_t *stage1;
+    const latok_stage1_t *stage1;
     const uint8_t *stage2;
     uint32_t low_limit, high_first, high_last, high_feat;
 };

@@ -1,5 +1,6 @@
 // Internal structures shared by the kernels (latok_kernels.cu) and the C-ABI host layer (latok_capi.cu).
 #pragma once
+#include "_gen/latok_table_types.h"   // latok_stage1_t (8 bits for UCD 11, 16 when a newer UCD needs more than 256 blocks)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -50,7 +51,7 @@ struct TableLayout {
     int lutv;         // u32[256]: 4 split-mask bytes for (value bit-plane 0 nibble | bit-plane 1 nibble << 4)
     int ascii_feat;   // u16[128]
     int class_feat;   // u16[16]
-    int stage1;       // u8[stage1_len]
+    int stage1;       // latok_stage1_t[stage1_len]
     int stage2;       // u8[stage2_len]
     int total;        // multiple of 16
     int stage1_len, stage2_len;

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(NTHREADS, kWords ? 1 : 2) tokenize_kernel(cons
     Tables tb;
     tb.ascii_feat = reinterpret_cast<const uint16_t *>(tableS + p.tl.ascii_feat);
     tb.class_feat = reinterpret_cast<const uint16_t *>(tableS + p.tl.class_feat);
-    tb.stage1 = tableS + p.tl.stage1;
+    tb.stage1 = reinterpret_cast<const latok_stage1_t *>(tableS + p.tl.stage1);
     tb.stage2 = tableS + p.tl.stage2;
     tb.low_limit = p.tl.low_limit; tb.high_first = p.tl.high_first; tb.high_last = p.tl.high_last; tb.high_feat = p.tl.high_feat;
     const uint32_t *lut0 = reinterpret_cast<const uint32_t *>(tableS + p.tl.lut3);

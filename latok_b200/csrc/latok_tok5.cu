@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     Tables tb;
     tb.ascii_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.ascii_feat - p.tl.lutv));
     tb.class_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.class_feat - p.tl.lutv));
-    tb.stage1 = tableS + (p.tl.stage1 - p.tl.lutv);
+    tb.stage1 = reinterpret_cast<const latok_stage1_t *>(tableS + (p.tl.stage1 - p.tl.lutv));
     tb.stage2 = p.table_blob + p.tl.stage2;
     tb.low_limit = p.tl.low_limit; tb.high_first = p.tl.high_first; tb.high_last = p.tl.high_last; tb.high_feat = p.tl.high_feat;
     const uint32_t *lutv = reinterpret_cast<const uint32_t *>(tableS);
@@ -1100,7 +1100,9 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 // token left open by earlier ranges
                 if (!lo_found && r > 0) {
                     const uint32_t PSr = (Sraw << 1) | pk_ps(pk);
-                    const uint32_t END = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo, last_range ? c_hi + 1 : c_hi);
+                    // (a range that ends at a closer also answers for the character after it: the next range begins at a
+                    // closer then and does not come here -- a token that covers this whole range may end exactly there)
+                    const uint32_t END = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo, (last_range || closed) ? c_hi + 1 : c_hi);
                     if (END) {
                         const int i = __ffs(END) - 1;
                         if (ktok + tp + __popc(E & mask_lt(i)) == 0) {

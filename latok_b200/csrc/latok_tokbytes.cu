@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) token_bytes_kernel(const TokBytesParams p
     Tables tb;
     tb.ascii_feat = reinterpret_cast<const uint16_t *>(p.table_blob + p.tl.ascii_feat);
     tb.class_feat = reinterpret_cast<const uint16_t *>(p.table_blob + p.tl.class_feat);
-    tb.stage1 = p.table_blob + p.tl.stage1; tb.stage2 = p.table_blob + p.tl.stage2;
+    tb.stage1 = reinterpret_cast<const latok_stage1_t *>(p.table_blob + p.tl.stage1); tb.stage2 = p.table_blob + p.tl.stage2;
     tb.low_limit = p.tl.low_limit; tb.high_first = p.tl.high_first; tb.high_last = p.tl.high_last; tb.high_feat = p.tl.high_feat;
     auto wp = [&](long long w) -> unsigned long long { return p.group_pref[w / TB_GROUP] + p.word_local[w]; };
     const long long nblk = (p.n_tokens + 31) / 32;

@@ -19,7 +19,8 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "_build" / "liblatok_oracle.so"
+# LATOK_ORACLE_LIB: an oracle built over other class ranges (tools/ucd_check.py checks a newer-UCD library with it)
+LIB_PATH = Path(os.environ.get("LATOK_ORACLE_LIB") or HERE / "_build" / "liblatok_oracle.so")
 NFEAT = 25
 
 # feature columns (latok/core/offsets.py:24-49)

@@ -298,3 +298,13 @@ def test_backlog_handoff_between_ranges(engine):
     # the same chunks with no space after them for a long while: the backlog is carried through several ranges
     long_tail = ["pre fix " + m + " " + ("word,word;word/" * 1200) + " end tail a b c" for m in marks]
     check_batch(engine, long_tail, 7, label="hand-off into a space-free run")
+
+
+def test_token_covering_a_whole_range(engine):
+    """A token (here: a whole string without a split point) that begins in one range, covers the next one completely
+    and ends within the closer search window of the third: the middle range must write its end.  Strings of 4-byte
+    characters a few bytes longer than a range drift through every alignment (found by tools/ucd_check.py)."""
+    texts = [chr(0x20000 + j) * n for j in range(700) for n in (997,)] + [chr(0x4E00 + j) * 1325 for j in range(500)]
+    texts += [chr(0x20000 + j) * n for j in range(300) for n in (993, 1001, 1012)]
+    check_batch(engine, texts, 3, label="token over a whole range")
+    check_batch(engine, texts[:400], 7, label="token over a whole range, token features")

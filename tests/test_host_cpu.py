@@ -299,3 +299,50 @@ def test_native_csv_reader_matches_python_csv_json(tmp_path):
                 list(r)
     with pytest.raises(ValueError):
         CsvReader(str(tmp_path / "missing.csv"))
+
+
+def _packed_table_lookup(header_text):
+    """Emulates the kernels' class look-up (latok_device.cuh: class_of_cp / mb_features) on the arrays of a generated
+    latok_tables.h; returns a function code point -> 12-bit feature word."""
+    def arr(name):
+        body = re.search(r"%s\[\d+\] = \{(.*?)\};" % name, header_text, re.S).group(1)
+        return [int(x, 0) for x in body.replace("\n", " ").split(",") if x.strip()]
+    low_limit = int(re.search(r"#define LATOK_TBL_LOW_LIMIT (0x[0-9A-Fa-f]+)u", header_text).group(1), 16)
+    ascii_feat, stage1, stage2, class_feat = arr("LATOK_ASCII_FEAT"), arr("LATOK_STAGE1"), arr("LATOK_STAGE2"), arr("LATOK_CLASS_FEAT")
+    high = [tuple(int(v, 16) for v in m) for m in re.findall(r"\{0x([0-9A-F]+)u, 0x([0-9A-F]+)u, 0x([0-9A-F]+)u\}", header_text)]
+    assert len(high) == 1
+
+    def look(cp):
+        if cp < 0x80:
+            return ascii_feat[cp]
+        if cp < low_limit:
+            b = stage2[stage1[cp >> 7] * 64 + ((cp & 127) >> 1)]
+            return class_feat[(b >> 4) if cp & 1 else (b & 15)]
+        return high[0][2] if high[0][0] <= cp <= high[0][1] else 0
+    return look, max(stage1)
+
+
+def test_packed_class_tables_cover_every_code_point():
+    """The packed two-stage table the kernels read (tools/gen_tables.py) against the class ranges it was built from,
+    for every code point: the UCD-11 table of the build, and a table generated for the UCD of the running Python
+    (tools/regen_classes.py; needs 16-bit stage-1 entries, which the kernels take from latok_table_types.h)."""
+    import subprocess
+    import sys
+    import tempfile
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root / "tools"))
+    import regen_classes as rc
+    gen = root / "latok_b200" / "csrc" / "_gen"
+    look, top = _packed_table_lookup((gen / "latok_tables.h").read_text())
+    want = rc.read_ranges(rc.UCD11)
+    assert all(look(cp) == want[cp] for cp in range(0x110000))
+    assert top < 256 and "typedef uint8_t latok_stage1_t" in (gen / "latok_table_types.h").read_text()
+    with tempfile.TemporaryDirectory() as d:
+        out = Path(d) / "ucd_new.txt"
+        subprocess.run([sys.executable, str(root / "tools" / "regen_classes.py"), "--out", str(out)], check=True)
+        env = dict(os.environ, LATOK_CLASSES=str(out), LATOK_LOW_LIMIT="0x32400")
+        subprocess.run([sys.executable, str(root / "tools" / "gen_tables.py"), d], check=True, env=env, stdout=subprocess.DEVNULL)
+        look, top = _packed_table_lookup((Path(d) / "latok_tables.h").read_text())
+        want = rc.read_ranges(out)
+        assert all(look(cp) == want[cp] for cp in range(0x110000))
+        assert ("typedef uint16_t latok_stage1_t" in (Path(d) / "latok_table_types.h").read_text()) == (top >= 256)

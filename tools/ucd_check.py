@@ -1,0 +1,34 @@
+#!/usr/bin/env python3
+"""Parity of a library built for ANOTHER Unicode version (tools/regen_classes.py + gen_tables.py) against
+an oracle built over the same class ranges: every code point (in strings of consecutive code points, with and without
+separators) + fuzz, all outputs.  Run on a GPU box:
+
+    LATOK_B200_LIB=<library> LATOK_ORACLE_LIB=<oracle .so> python tools/ucd_check.py
+"""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np
+import corpus
+from oracle import oracle
+from latok_b200.engine import Engine
+
+cps = [c for c in range(0x110000) if not 0xD800 <= c <= 0xDFFF]
+texts = ["".join(map(chr, cps[i:i + 997])) for i in range(0, len(cps), 997)]
+texts += [" ".join(map(chr, cps[i:i + 500])) for i in range(0, len(cps), 500)]
+texts += ["a".join(map(chr, cps[i:i + 301])) + " A@b " for i in range(0, len(cps), 301)]
+texts += corpus.fuzz_strings(51, 3000, 200, "mixed")
+texts = [t for t in texts if t]
+o = oracle.tokenize_batch(texts, matrix=True, feats=True)
+with Engine(0) as e:
+    for what in (3, 7, 15):
+        r = e.run(texts, what)
+        assert np.array_equal(r.splits, o["splits"]) and np.array_equal(r.spans, o["spans"]), what
+        assert np.array_equal(r.tok_offsets, o["tok_offsets"]) and np.array_equal(r.char_offsets, o["char_offsets"]), what
+        if what & 4:
+            assert np.array_equal(r.tok_feats, o["tok_feats"]), what
+        if what & 8:
+            assert np.array_equal(r.matrix, o["matrix"]), what
+print(f"ucd check ok: {len(texts)} strings, {o['n_chars']} characters, {o['n_tokens']} tokens; "
+      f"feature word of U+31350 (CJK extension H, new after UCD 11): {oracle.base_features(0x31350):03X}")
