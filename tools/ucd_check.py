@@ -4,6 +4,17 @@ an oracle built over the same class ranges: every code point (in strings of cons
 separators) + fuzz, all outputs.  Run on a GPU box:
 
     LATOK_B200_LIB=<library> LATOK_ORACLE_LIB=<oracle .so> python tools/ucd_check.py
+
+Building the pair for the UCD of the running Python (on the CPU box; put both files somewhere inside the repository so
+that they travel to the GPU box, e.g. latok_b200/_variants/, which is git-ignored):
+
+    python tools/regen_classes.py --out /tmp/ucd.txt
+    LATOK_CLASSES=/tmp/ucd.txt LATOK_LOW_LIMIT=0x32400 LATOK_B200_LIB_OUT=$PWD/latok_b200/_variants/liblatok_ucd.so \
+        python -m latok_b200.build                       # library with the new tables (then rebuild the default one!)
+    LATOK_CLASSES=/tmp/ucd.txt LATOK_LOW_LIMIT=0x32400 python tools/gen_tables.py /tmp/gen
+    mkdir -p /tmp/orc/_gen && cp oracle/latok_oracle.c /tmp/orc/ && cp /tmp/gen/oracle_runs.h /tmp/orc/_gen/
+    gcc -O2 -shared -fPIC /tmp/orc/latok_oracle.c -o latok_b200/_variants/liblatok_oracle_ucd.so
+    python -m latok_b200.build                           # back to the UCD-11 tables of the parity tests
 """
 import sys
 from pathlib import Path
