@@ -11,7 +11,8 @@
  *     failure on the calling thread is latok_b200_last_error().  This replaces
  *     PyErr_SetString(PyExc_ValueError, ...) + NULL (latok.c:40-50,151-171,292-312).
  *   - an engine owns one device, its streams, the Unicode class table and all device / pinned
- *     staging memory.  An engine is not thread-safe; use one engine (and host thread) per GPU.
+ *     staging memory.  An engine is not thread-safe: one host thread at a time (the Python
+ *     wrapper holds a lock per engine); use one engine per GPU.
  *   - text is a flat UTF-8 byte buffer plus an int64 offsets array of n_strings+1 entries
  *     (offsets[0]==0, non-decreasing, offsets[n_strings]==total bytes).  The bytes must be
  *     well-formed UTF-8; lone surrogates encoded the way Python's 'surrogatepass' does are
@@ -37,7 +38,7 @@ extern "C" {
 #define LATOK_B200_API
 #endif
 
-#define LATOK_B200_ABI_VERSION 1
+#define LATOK_B200_ABI_VERSION 2
 #define LATOK_B200_NUM_FEATURES 25 /* FEATURE_COUNT, latok.h:49 / offsets.py:49 */
 
 enum {
@@ -54,7 +55,9 @@ enum {
     LATOK_B200_SPLITS = 1, /* int8 split mask per character    (gen_split_mask, default_tokenizer.py:113-134) */
     LATOK_B200_SPANS = 2,  /* token spans + per-string CSR      (tokenize/featurize loop, :148-158,:174-191)   */
     LATOK_B200_FEATS = 4,  /* int8[T,25] per-token feature sums (featurize, :181-191 -> latok.c:342-354)       */
-    LATOK_B200_MATRIX = 8  /* int8[C,25] feature matrix         (_gen_parse_matrix, latok.c:31-138)            */
+    LATOK_B200_MATRIX = 8, /* int8[C,25] feature matrix         (_gen_parse_matrix, latok.c:31-138)            */
+    LATOK_B200_SPANS16 = 16 /* compact results: spans come back as uint16[T,2] (half the device -> host bytes);
+                               implies SPANS; fetch fails with EINVAL if a string has >= 65 536 characters          */
 };
 
 typedef struct latok_b200_engine latok_b200_engine;
@@ -82,33 +85,50 @@ LATOK_B200_API int latok_b200_set_rules(latok_b200_engine *e,
                          const int8_t *mask, int mask_rows, int mask_cols,
                          const int8_t *sym, int sym_rows, int sym_cols);
 
-/* ---- batch hot path --------------------------------------------------------------------- */
-/* Host buffers in: packs into pinned staging, streams to the device (cudaMemcpyAsync) and
- * launches the kernels.  Returns once the work is enqueued. */
+/* ---- batch hot path ---------------------------------------------------------------------
+ * A submitted batch lives in one of the engine's TWO sets of device / pinned staging buffers until it is released.
+ * Pipeline depth 1 (default): every submit replaces the batch in flight; sizes / fetch refer to it.
+ * Pipeline depth 2: two batches may be in flight; sizes / fetch / fetch_token_bytes / last_stats refer to the OLDEST
+ * one and latok_b200_release() retires it.  The loop
+ *     submit(0); for i: { submit(i+1); fetch(i); release(); }
+ * on ONE host thread overlaps the host -> device copy and the kernels of batch i+1 with the device -> host copy of
+ * batch i (separate copy-in, compute and copy-out streams; this is the double buffering of the north star). */
+LATOK_B200_API int latok_b200_set_pipeline_depth(latok_b200_engine *e, int depth);
+/* Host buffers in: stages pageable memory through the set's pinned buffers (pinned caller memory, e.g. from
+ * latok_b200_host_alloc, goes straight to the device), cudaMemcpyAsync on the copy-in stream, kernels on the compute
+ * stream.  Returns once the work is enqueued.  ESTATE if `depth` batches are already in flight. */
 LATOK_B200_API int latok_b200_submit(latok_b200_engine *e, const uint8_t *utf8, const int64_t *offsets,
                       int64_t n_strings, uint32_t what);
 /* Same, for text already resident in device memory (16-byte aligned d_utf8). */
 LATOK_B200_API int latok_b200_submit_device(latok_b200_engine *e, const uint8_t *d_utf8, const int64_t *d_offsets,
                              int64_t n_strings, int64_t n_bytes, uint32_t what);
-/* Waits for the submitted batch; C = total characters, T = total emitted tokens. */
+/* Waits for the kernels of the (oldest) batch in flight; C = total characters, T = total emitted tokens. */
 LATOK_B200_API int latok_b200_sizes(latok_b200_engine *e, int64_t *n_chars, int64_t *n_tokens);
-/* Copies results into caller (host) buffers; any pointer may be NULL to skip that output.
+/* Copies results into caller (host) buffers on the copy-out stream and waits for them; any pointer may be NULL to
+ * skip that output.  cap_chars / cap_tokens / cap_strings = what the caller's arrays have room for (characters,
+ * tokens, strings); EINVAL (nothing is written) when the batch needs more.
  *   splits       int8  [C]      split mask, values 0..n (counts, not booleans)
  *   char_offsets int64 [S+1]    first character of each string in `splits` / `matrix`
  *   spans        int32 [T,2]    (start_idx, end_idx) per token, untrimmed, string-relative
+ *                               (uint16 [T,2] when LATOK_B200_SPANS16 was requested)
  *   tok_offsets  int64 [S+1]    first token of each string in `spans` / `tok_feats`
  *   tok_feats    int8  [T,25]   per-token feature sums (uint8 wrap-around viewed as int8)
  *   matrix       int8  [C,25]   the parse matrix
  */
-LATOK_B200_API int latok_b200_fetch(latok_b200_engine *e, int8_t *splits, int64_t *char_offsets, int32_t *spans,
-                     int64_t *tok_offsets, int8_t *tok_feats, int8_t *matrix);
+LATOK_B200_API int latok_b200_fetch(latok_b200_engine *e, int64_t cap_chars, int64_t cap_tokens, int64_t cap_strings,
+                     int8_t *splits, int64_t *char_offsets, void *spans, int64_t *tok_offsets, int8_t *tok_feats,
+                     int8_t *matrix);
+/* Retires the oldest batch in flight (its set may be submitted into again). */
+LATOK_B200_API int latok_b200_release(latok_b200_engine *e);
+LATOK_B200_API int latok_b200_in_flight(latok_b200_engine *e, int *n);
 /* Token spans as BYTE ranges of the flat UTF-8 buffer, trimmed the way the reference trims a token with
  * `text[s:e].strip()` (default_tokenizer.py:151-158): utf8[byte_spans[2k] : byte_spans[2k+1]] is the
  * text of token k, so tokens can be sliced from the packed buffer (or viewed as an Arrow-style string array)
  * without touching Python strings.  Needs LATOK_B200_SPANS at submit and the submitted text still in place
  * (host submits: until the next submit; device submits: the caller's buffer).  byte_spans is int64 [T,2] in host
- * memory, or in device memory when on_device != 0.  Runs three small kernels after the tokenize kernel. */
-LATOK_B200_API int latok_b200_fetch_token_bytes(latok_b200_engine *e, int64_t *byte_spans, int on_device);
+ * memory, or in device memory when on_device != 0, with room for cap_tokens tokens (EINVAL if the batch has more).
+ * Runs three small kernels after the tokenize kernel. */
+LATOK_B200_API int latok_b200_fetch_token_bytes(latok_b200_engine *e, int64_t cap_tokens, int64_t *byte_spans, int on_device);
 /* device time of those kernels for the last call (harness) */
 LATOK_B200_API int latok_b200_token_bytes_ms(latok_b200_engine *e, float *ms);
 /* Device pointers of the same results (valid until the next submit); for device-side consumers. */

@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("LATOK_B200_LIB") or PKG / "liblatok_b200.so")  # override: development builds only
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, EINTERNAL = range(6)
-SPLITS, SPANS, FEATS, MATRIX = 1, 2, 4, 8
+SPLITS, SPANS, FEATS, MATRIX, SPANS16 = 1, 2, 4, 8, 16
 NUM_FEATURES = 25
 
 
@@ -46,8 +46,11 @@ def load():
         "latok_b200_submit": (C.c_int, [vp, vp, vp, i64, u32]),
         "latok_b200_submit_device": (C.c_int, [vp, vp, vp, i64, i64, u32]),
         "latok_b200_sizes": (C.c_int, [vp, P(i64), P(i64)]),
-        "latok_b200_fetch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
-        "latok_b200_fetch_token_bytes": (C.c_int, [vp, vp, i32]),
+        "latok_b200_set_pipeline_depth": (C.c_int, [vp, i32]),
+        "latok_b200_fetch": (C.c_int, [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp]),
+        "latok_b200_release": (C.c_int, [vp]),
+        "latok_b200_in_flight": (C.c_int, [vp, P(C.c_int)]),
+        "latok_b200_fetch_token_bytes": (C.c_int, [vp, i64, vp, i32]),
         "latok_b200_token_bytes_ms": (C.c_int, [vp, P(C.c_float)]),
         "latok_b200_device_results": (C.c_int, [vp, P(vp), P(vp), P(vp), P(vp), P(vp), P(vp)]),
         "latok_b200_timer_begin": (C.c_int, [vp]),
@@ -66,7 +69,7 @@ def load():
     for name, (res, args) in proto.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
-    if L.latok_b200_abi_version() != 1:
+    if L.latok_b200_abi_version() != 2:
         raise ImportError("liblatok_b200.so ABI version mismatch; rebuild with python -m latok_b200.build")
     _lib = L
     return L

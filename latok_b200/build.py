@@ -36,6 +36,30 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found; liblatok_b200.so cannot be built (there is no CPU fallback)")
 
 
+PYPACK_SRC = CSRC / "latok_pypack.c"
+
+
+def pypack_path() -> Path:
+    import sysconfig
+    return PKG / ("_pypack" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_pypack(force: bool = False, verbose: bool = False) -> Path:
+    """The CPython shim that packs list[str] into UTF-8 + offsets (host code, gcc)."""
+    import sysconfig
+    out = pypack_path()
+    if not force and out.exists() and out.stat().st_mtime >= PYPACK_SRC.stat().st_mtime:
+        return out
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("gcc not found; _pypack cannot be built")
+    cmd = [cc, "-O3", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"], str(PYPACK_SRC), "-o", str(out)]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def _stale() -> bool:
     if not LIB.exists():
         return True
@@ -69,3 +93,4 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 if __name__ == "__main__":
     path = build_library(force=True, verbose="--verbose" in sys.argv or "-v" in sys.argv)
     print(path)
+    print(build_pypack(force=True, verbose="--verbose" in sys.argv or "-v" in sys.argv))

@@ -83,7 +83,10 @@ def batch_arrays(texts: Sequence[str], splits=True, spans=True, feats=False, mat
 
 
 def _token_texts(text: str, spans: np.ndarray) -> List[str]:
-    return [text[s:e].strip() for s, e in spans]
+    # `if token` as in the reference's loop (default_tokenizer.py:152-158): the kernel already drops the spans that
+    # are one whitespace character, the guard keeps the two in step should a class table's SPACE set ever differ
+    # from str.strip()'s (tests/test_host_cpu.py checks that they agree for the shipped table)
+    return [tok for tok in (text[s:e].strip() for s, e in spans) if tok]
 
 
 def tokenize_batch(texts: Sequence[str], engine=None) -> List[List[str]]:
@@ -127,9 +130,10 @@ def tokenize_packed(buf: np.ndarray, offsets: np.ndarray, engine=None) -> Packed
     """Packed UTF-8 in (flat uint8 buffer + int64 offsets[S+1]), token byte ranges out; no Python loop per token."""
     e = engine or default_engine()
     buf = np.ascontiguousarray(buf, dtype=np.uint8)
-    e.submit(buf, offsets, SPANS)
-    r = e.fetch()
-    return PackedTokens(buf, e.token_bytes(), r.tok_offsets)
+    with e._lock:                                    # submit .. fetch .. byte ranges of the same batch
+        e.submit(buf, offsets, SPANS)
+        r = e.fetch()
+        return PackedTokens(buf, e.token_bytes(), r.tok_offsets)
 
 
 def featurize_batch(texts: Sequence[str], engine=None) -> List[List[LaToken]]:
@@ -137,7 +141,8 @@ def featurize_batch(texts: Sequence[str], engine=None) -> List[List[LaToken]]:
     out = []
     for i, t in enumerate(texts):
         sp, ft = r.string_spans(i), r.string_feats(i)
-        out.append([LaToken(t[s:e].strip(), int(s), int(e), ft[k].copy()) for k, (s, e) in enumerate(sp)])
+        out.append([LaToken(tok, int(s), int(e), ft[k].copy())
+                    for k, (s, e) in enumerate(sp) for tok in (t[s:e].strip(),) if tok])
     return out
 
 
@@ -152,7 +157,9 @@ def tokenize(text: str):
         raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # reference: splits[0] = 1, :132
     r = batch_arrays([text], splits=False, spans=True)
     for s, e in r.spans:
-        yield text[s:e].strip()
+        token = text[s:e].strip()
+        if token:                                    # default_tokenizer.py:152-158
+            yield token
 
 
 def featurize(text: str):
@@ -161,4 +168,6 @@ def featurize(text: str):
         raise IndexError("index 0 is out of bounds for axis 0 with size 0")
     r = batch_arrays([text], splits=False, spans=True, feats=True)
     for k, (s, e) in enumerate(r.spans):
-        yield LaToken(text[s:e].strip(), int(s), int(e), r.tok_feats[k].copy())
+        token = text[s:e].strip()
+        if token:                                    # default_tokenizer.py:175-191
+            yield LaToken(token, int(s), int(e), r.tok_feats[k].copy())

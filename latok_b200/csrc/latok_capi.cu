@@ -116,19 +116,48 @@ bool same_rows(const uint32_t *a, int na, const uint32_t *b, int nb)
 
 }  // namespace
 
+// One of the two sets of buffers a submitted batch lives in until it has been fetched.  Two sets alternate, so that
+// (pipeline depth 2) batch i+1 is copied in and tokenized while batch i is copied out.
+struct Batch {
+    DevBuf<uint8_t> d_in;
+    DevBuf<long long> d_off, d_first, d_char_off, d_tok_off;
+    DevBuf<int8_t> d_splits, d_feats, d_matrix;
+    DevBuf<int32_t> d_spans;
+    DevBuf<uint32_t> d_spans16;                     // LATOK_B200_SPANS16: (start | end << 16) per token
+    DevBuf<Result> d_result;
+    PinBuf<Result> h_result;
+    PinBuf<uint8_t> h_in;                           // pinned staging of pageable caller buffers
+    PinBuf<long long> h_off;
+    cudaEvent_t ev_h2d = nullptr;                   // inputs have arrived on the device (copy-in stream)
+    cudaEvent_t ev_index = nullptr;                 // string index built (aux stream)
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around the tokenize kernel (timing)
+    cudaEvent_t ev_kdone = nullptr;                 // last device work that touches this set (compute stream)
+    bool submitted = false, sized = false, inputs_on_stream = false;
+    const uint8_t *cur_in = nullptr;
+    const long long *cur_off = nullptr;
+    long long n_strings = 0, n_bytes = 0;
+    uint32_t what = 0;
+    long long n_chars = 0, n_tokens = 0, walks = 0;
+    float kernel_ms = 0.f;
+    void release()
+    {
+        d_in.release(); d_off.release(); d_first.release(); d_char_off.release(); d_tok_off.release();
+        d_splits.release(); d_feats.release(); d_matrix.release(); d_spans.release(); d_spans16.release();
+        d_result.release(); h_result.release(); h_in.release(); h_off.release();
+        for (cudaEvent_t *ev : {&ev_h2d, &ev_index, &ev_k0, &ev_k1, &ev_kdone}) { if (*ev) cudaEventDestroy(*ev); *ev = nullptr; }
+    }
+};
+
 struct latok_b200_engine {
     int device = 0;
     int n_sm = 0;
-    cudaStream_t stream = nullptr, aux = nullptr;   // aux: string index of the next batch while the previous one is tokenized
-    cudaEvent_t ev_in = nullptr, ev_index[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    int slot = 0;                                   // which of the two index / result sets the current batch uses
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
+    // compute: kernels; aux: string index of the next batch while the previous one is tokenized;
+    // s_in / s_out: host -> device and device -> host copies (PCIe is full duplex: the three overlap)
+    cudaStream_t stream = nullptr, aux = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
     TableLayout tl{};
     RuleSet rules{};
-    DevBuf<uint8_t> d_table, d_in, d_scratch, d_scratch2, d_scratch3;
-    DevBuf<long long> d_off, d_first[2], d_char_off, d_tok_off;
-    DevBuf<int8_t> d_splits, d_feats, d_matrix;
-    DevBuf<int32_t> d_spans;
+    DevBuf<uint8_t> d_table, d_scratch, d_scratch2, d_scratch3;
     DevBuf<AggRec> agg;
     DevBuf<IncRec> inc;
     DevBuf<OpenSums> osum;
@@ -138,20 +167,13 @@ struct latok_b200_engine {
     DevBuf<unsigned> d_blk_local, d_group_tot;
     DevBuf<unsigned long long> d_group_pref;
     float last_token_bytes_ms = 0.f;
-    DevBuf<Result> d_result[2];
-    PinBuf<uint8_t> h_in;
-    PinBuf<long long> h_off;
-    PinBuf<Result> h_result[2];
     unsigned epoch = 0;
     long long launches = 0;
-    // current batch
-    bool submitted = false, sized = false, inputs_on_stream = false;
-    const uint8_t *cur_in = nullptr;
-    const long long *cur_off = nullptr;
-    long long n_strings = 0, n_bytes = 0;
-    uint32_t what = 0;
-    long long n_chars = 0, n_tokens = 0, walks = 0;
-    float last_kernel_ms = 0.f;
+    Batch set[2];
+    int depth = 1;                                  // batches that may be in flight (submitted, not yet released)
+    int q[2] = {0, 0}, nq = 0;                      // the sets in flight, oldest first
+    int last = 1;                                   // set of the most recent submit
+    Batch *front() { return nq ? &set[q[0]] : nullptr; }
 };
 
 // for the other translation units of the library (latok_reader.cpp)
@@ -253,31 +275,29 @@ int latok_b200_create(int device, size_t max_batch_bytes, int64_t max_strings, l
     int rc = [&]() -> int {
         CU(cudaSetDevice(device));
         CU(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
-        CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking));
-        CU(cudaEventCreate(&e->ev_k0)); CU(cudaEventCreate(&e->ev_k1));
-        CU(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
-        for (int i = 0; i < 2; ++i) {
-            CU(cudaEventCreateWithFlags(&e->ev_index[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
-        }
+        for (cudaStream_t *st : {&e->stream, &e->aux, &e->s_in, &e->s_out}) CU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
         CU(cudaEventCreate(&e->ev_t0)); CU(cudaEventCreate(&e->ev_t1));
         CU(cudaEventCreate(&e->ev_b0)); CU(cudaEventCreate(&e->ev_b1));
         if (int r = build_table(e)) return r;
         e->rules = default_rules();
-        for (int i = 0; i < 2; ++i) {
-            if (int r = e->d_result[i].ensure(1, true)) return r;
-            if (int r = e->h_result[i].ensure(1)) return r;
+        for (Batch &b : e->set) {
+            CU(cudaEventCreate(&b.ev_k0)); CU(cudaEventCreate(&b.ev_k1));
+            for (cudaEvent_t *ev : {&b.ev_h2d, &b.ev_index, &b.ev_kdone}) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+            if (int r = b.d_result.ensure(1, true)) return r;
+            if (int r = b.h_result.ensure(1)) return r;
         }
+        // max_batch_bytes / max_strings pre-size the first set (a second one is sized on first use, i.e. by a
+        // pipelined caller or by back-to-back submits)
+        Batch &b = e->set[0];
         if (max_batch_bytes) {
-            if (int r = e->d_in.ensure(max_batch_bytes + 64)) return r;
-            if (int r = e->d_splits.ensure(max_batch_bytes + 64)) return r;
-            if (int r = e->d_spans.ensure(2 * (max_batch_bytes / 3 + 1024))) return r;
+            if (int r = b.d_in.ensure(max_batch_bytes + 64)) return r;
+            if (int r = b.d_splits.ensure(max_batch_bytes + 64)) return r;
+            if (int r = b.d_spans.ensure(2 * (max_batch_bytes / 3 + 1024))) return r;
         }
         if (max_strings) {
-            if (int r = e->d_off.ensure((size_t)max_strings + 1)) return r;
-            if (int r = e->d_char_off.ensure((size_t)max_strings + 1)) return r;
-            if (int r = e->d_tok_off.ensure((size_t)max_strings + 1)) return r;
+            if (int r = b.d_off.ensure((size_t)max_strings + 1)) return r;
+            if (int r = b.d_char_off.ensure((size_t)max_strings + 1)) return r;
+            if (int r = b.d_tok_off.ensure((size_t)max_strings + 1)) return r;
         }
         return 0;
     }();
@@ -290,26 +310,23 @@ int latok_b200_destroy(latok_b200_engine *e)
 {
     if (!e) return LATOK_B200_OK;
     cudaSetDevice(e->device);
-    if (e->stream) cudaStreamSynchronize(e->stream);
-    if (e->aux) cudaStreamSynchronize(e->aux);
-    e->d_table.release(); e->d_in.release(); e->d_scratch.release(); e->d_scratch2.release(); e->d_scratch3.release();
-    e->d_off.release(); e->d_first[0].release(); e->d_first[1].release(); e->d_char_off.release(); e->d_tok_off.release();
-    e->d_splits.release(); e->d_feats.release(); e->d_matrix.release(); e->d_spans.release();
+    for (cudaStream_t st : {e->stream, e->aux, e->s_in, e->s_out}) if (st) cudaStreamSynchronize(st);
+    e->d_table.release(); e->d_scratch.release(); e->d_scratch2.release(); e->d_scratch3.release();
     e->agg.release(); e->inc.release(); e->osum.release(); e->d_planes.release(); e->span_scratch.release();
     e->d_tok_bytes.release(); e->d_blk_local.release(); e->d_group_tot.release(); e->d_group_pref.release();
-    e->d_result[0].release(); e->d_result[1].release();
-    e->h_in.release(); e->h_off.release(); e->h_result[0].release(); e->h_result[1].release();
-    if (e->ev_in) cudaEventDestroy(e->ev_in);
-    for (int i = 0; i < 2; ++i) { if (e->ev_index[i]) cudaEventDestroy(e->ev_index[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); }
-    if (e->aux) cudaStreamDestroy(e->aux);
-    if (e->ev_k0) cudaEventDestroy(e->ev_k0);
-    if (e->ev_k1) cudaEventDestroy(e->ev_k1);
-    if (e->ev_t0) cudaEventDestroy(e->ev_t0);
-    if (e->ev_b0) cudaEventDestroy(e->ev_b0);
-    if (e->ev_b1) cudaEventDestroy(e->ev_b1);
-    if (e->ev_t1) cudaEventDestroy(e->ev_t1);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    for (Batch &b : e->set) b.release();
+    for (cudaEvent_t ev : {e->ev_t0, e->ev_t1, e->ev_b0, e->ev_b1}) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : {e->stream, e->aux, e->s_in, e->s_out}) if (st) cudaStreamDestroy(st);
     delete e;
+    return LATOK_B200_OK;
+}
+
+int latok_b200_set_pipeline_depth(latok_b200_engine *e, int depth)
+{
+    if (!e) return fail(LATOK_B200_EINVAL, "engine is NULL");
+    if (depth != 1 && depth != 2) return fail(LATOK_B200_EINVAL, "pipeline depth must be 1 or 2");
+    if (e->nq > 1) return fail(LATOK_B200_ESTATE, "two batches are in flight; release them before changing the pipeline depth");
+    e->depth = depth;
     return LATOK_B200_OK;
 }
 
@@ -339,28 +356,43 @@ int latok_b200_set_rules(latok_b200_engine *e, const int8_t *split, int sr, int 
     return LATOK_B200_OK;
 }
 
-static int run_device(latok_b200_engine *e)
+// narrows the int32 (start, end) pairs of the tokenize kernel to one uint32 (start | end << 16) per token
+// (LATOK_B200_SPANS16: half the device -> host bytes when every string has fewer than 65 536 characters)
+__global__ void narrow_spans_kernel(const int2 *spans, uint32_t *out, Result *res, long long cap)
 {
-    // token-feature / matrix modes run the v4 kernel (one CTA per 7 936-byte tile); split mask + spans run v5 (one warp
-    // per 3 968-byte range, V5_NW ranges per tile)
-    const bool words = (e->what & LATOK_B200_MATRIX) != 0, feats = (e->what & LATOK_B200_FEATS) != 0;
+    const long long n = min((long long)res->n_tokens, cap);
+    bool over = false;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int2 v = spans[k];
+        over |= ((unsigned)v.x | (unsigned)v.y) > 0xFFFFu;
+        out[k] = ((unsigned)v.x & 0xFFFFu) | ((unsigned)v.y << 16);
+    }
+    if (over) atomicOr(&res->error, 16u);
+}
+
+static int run_device(latok_b200_engine *e, Batch &b)
+{
+    // the matrix mode runs the v4 kernel (one CTA per 7 936-byte tile); everything else (split mask, spans, token
+    // features) runs v5 (one warp per 3 968-byte range, V5_NW ranges per tile)
+    const bool words = (b.what & LATOK_B200_MATRIX) != 0, feats = (b.what & LATOK_B200_FEATS) != 0;
     const bool use5 = !words && !getenv("LATOK_B200_FORCE_V4");
     const int unit = use5 ? V5_RANGE : TILE;
-    const long long nunits = e->n_bytes / unit + 1;
+    const long long nunits = b.n_bytes / unit + 1;
     const long long ntiles = use5 ? (nunits + V5_NW - 1) / V5_NW : nunits;
-    const int slot = e->slot ^= 1;
-    if (int r = e->d_first[slot].ensure((size_t)nunits + 1)) return r;
+    if (int r = b.d_first.ensure((size_t)nunits + 1)) return r;
     // the status word of every aggregate record carries the launch epoch, so records are zeroed only when (re)allocated
-    if ((size_t)ntiles > e->agg.cap) { if (int r = e->agg.ensure((size_t)ntiles, true)) return r; }
-    if (int r = e->inc.ensure((size_t)ntiles)) return r;
-    if (feats) { if (int r = e->osum.ensure((size_t)(use5 ? nunits : ntiles), true)) return r; }
-    if (feats && use5) { if (int r = e->d_planes.ensure(tokenize5_plane_words(nunits))) return r; }
-    if (int r = e->d_splits.ensure((size_t)e->n_bytes + 64)) return r;
-    if (int r = e->d_char_off.ensure((size_t)e->n_strings + 1)) return r;
-    if (int r = e->d_tok_off.ensure((size_t)e->n_strings + 1)) return r;
-    if (e->d_spans.cap < 2048) { if (int r = e->d_spans.ensure(2 * ((size_t)e->n_bytes / 3 + 1024))) return r; }
-    if (e->what & LATOK_B200_FEATS) { if (int r = e->d_feats.ensure((e->d_spans.cap / 2) * NFEAT)) return r; }
-    if (e->what & LATOK_B200_MATRIX) { if (int r = e->d_matrix.ensure(((size_t)e->n_bytes + 64) * NFEAT)) return r; }
+    // (agg / inc / osum / planes are shared by the two sets: tokenize kernels run one after the other on one stream)
+    if ((size_t)ntiles > e->agg.cap) { CU(cudaStreamSynchronize(e->stream)); if (int r = e->agg.ensure((size_t)ntiles, true)) return r; }
+    if ((size_t)ntiles > e->inc.cap) { CU(cudaStreamSynchronize(e->stream)); if (int r = e->inc.ensure((size_t)ntiles)) return r; }
+    if (feats && (size_t)(use5 ? nunits : ntiles) > e->osum.cap) { CU(cudaStreamSynchronize(e->stream)); if (int r = e->osum.ensure((size_t)(use5 ? nunits : ntiles), true)) return r; }
+    if (feats && use5 && tokenize5_plane_words(nunits) > e->d_planes.cap) { CU(cudaStreamSynchronize(e->stream)); if (int r = e->d_planes.ensure(tokenize5_plane_words(nunits))) return r; }
+    if (int r = b.d_splits.ensure((size_t)b.n_bytes + 64)) return r;
+    if (int r = b.d_char_off.ensure((size_t)b.n_strings + 1)) return r;
+    if (int r = b.d_tok_off.ensure((size_t)b.n_strings + 1)) return r;
+    if (b.d_spans.cap < 2048) { if (int r = b.d_spans.ensure(2 * ((size_t)b.n_bytes / 3 + 1024))) return r; }
+    if (b.what & LATOK_B200_FEATS) { if (int r = b.d_feats.ensure((b.d_spans.cap / 2) * NFEAT)) return r; }
+    if (b.what & LATOK_B200_MATRIX) { if (int r = b.d_matrix.ensure(((size_t)b.n_bytes + 64) * NFEAT)) return r; }
+    if (b.what & LATOK_B200_SPANS16) { if (int r = b.d_spans16.ensure(b.d_spans.cap / 2)) return r; }
 
     e->epoch = (e->epoch + 1) & 0x3FFFFFFFu;
     if (e->epoch == 0) {  // wrapped: clear stale status words
@@ -369,15 +401,15 @@ static int run_device(latok_b200_engine *e)
     }
     Params p;
     memset(&p, 0, sizeof p);
-    p.in = e->cur_in; p.n_bytes = e->n_bytes; p.offsets = e->cur_off; p.n_strings = e->n_strings;
-    p.tile_first_str = e->d_first[slot].p; p.ntiles = ntiles; p.nranges = nunits;
-    p.splits = e->d_splits.p; p.char_off = e->d_char_off.p; p.spans = e->d_spans.p; p.tok_off = e->d_tok_off.p;
-    p.feats = e->d_feats.p; p.matrix = e->d_matrix.p;
-    p.cap_tokens = (long long)(e->d_spans.cap / 2);
-    p.what = e->what;
-    p.agg = e->agg.p; p.inc = e->inc.p; p.osum = e->osum.p; p.planes = e->d_planes.p; p.span_scratch = e->span_scratch.p; p.epoch = e->epoch;
-    p.ticket = &e->d_result[slot].p->ticket; p.ticket_base = 0;
-    p.result = e->d_result[slot].p;
+    p.in = b.cur_in; p.n_bytes = b.n_bytes; p.offsets = b.cur_off; p.n_strings = b.n_strings;
+    p.tile_first_str = b.d_first.p; p.ntiles = ntiles; p.nranges = nunits;
+    p.splits = b.d_splits.p; p.char_off = b.d_char_off.p; p.spans = b.d_spans.p; p.tok_off = b.d_tok_off.p;
+    p.feats = b.d_feats.p; p.matrix = b.d_matrix.p;
+    p.cap_tokens = (long long)(b.d_spans.cap / 2);
+    p.what = b.what & 15u;
+    p.agg = e->agg.p; p.inc = e->inc.p; p.osum = e->osum.p; p.planes = e->d_planes.p; p.epoch = e->epoch;
+    p.ticket = &b.d_result.p->ticket; p.ticket_base = 0;
+    p.result = b.d_result.p;
     p.table_blob = e->d_table.p; p.tl = e->tl; p.rules = e->rules;
     int grid = e->n_sm * (use5 ? tokenize5_ctas_per_sm(e->tl, e->rules.is_default != 0, feats)
                                : tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words, feats));
@@ -386,32 +418,49 @@ static int run_device(latok_b200_engine *e)
     p.span_scratch = e->span_scratch.p;
 
     // The string index of this batch is built on the aux stream, so that with back-to-back submits it overlaps the
-    // tokenize kernel of the previous batch (two index / result sets alternate).
-    if (e->inputs_on_stream) {                       // host submit: the offsets arrive by a copy on the main stream
-        CU(cudaEventRecord(e->ev_in, e->stream));
-        CU(cudaStreamWaitEvent(e->aux, e->ev_in, 0));
-    }
-    CU(cudaStreamWaitEvent(e->aux, e->ev_done[slot], 0));     // this set's previous batch has been tokenized and read back
-    CU(cudaMemsetAsync(e->d_result[slot].p, 0, sizeof(Result), e->aux));
-    CU(launch_tile_index(e->cur_off, e->n_strings, e->n_bytes, e->d_first[slot].p, nunits, unit, e->d_result[slot].p, e->aux));
-    CU(cudaEventRecord(e->ev_index[slot], e->aux));
-    CU(cudaStreamWaitEvent(e->stream, e->ev_index[slot], 0));
-    CU(cudaEventRecord(e->ev_k0, e->stream));
+    // tokenize kernel of the previous batch (the two sets alternate).
+    if (b.inputs_on_stream) CU(cudaStreamWaitEvent(e->aux, b.ev_h2d, 0));    // host submit: the offsets arrive on the copy-in stream
+    CU(cudaStreamWaitEvent(e->aux, b.ev_kdone, 0));            // this set's previous batch has been tokenized
+    CU(cudaMemsetAsync(b.d_result.p, 0, sizeof(Result), e->aux));
+    CU(launch_tile_index(b.cur_off, b.n_strings, b.n_bytes, b.d_first.p, nunits, unit, b.d_result.p, e->aux));
+    CU(cudaEventRecord(b.ev_index, e->aux));
+    if (b.inputs_on_stream) CU(cudaStreamWaitEvent(e->stream, b.ev_h2d, 0));
+    CU(cudaStreamWaitEvent(e->stream, b.ev_index, 0));
+    CU(cudaEventRecord(b.ev_k0, e->stream));
     CU(use5 ? launch_tokenize5(p, grid, e->stream) : launch_tokenize(p, grid, e->stream));
-    CU(cudaEventRecord(e->ev_k1, e->stream));
-    CU(cudaMemcpyAsync(e->h_result[slot].p, e->d_result[slot].p, sizeof(Result), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaEventRecord(e->ev_done[slot], e->stream));
+    CU(cudaEventRecord(b.ev_k1, e->stream));
     e->launches += 2;
-    e->submitted = true;
-    e->sized = false;
+    if (b.what & LATOK_B200_SPANS16) {
+        narrow_spans_kernel<<<e->n_sm * 8, 256, 0, e->stream>>>(reinterpret_cast<const int2 *>(b.d_spans.p), b.d_spans16.p, b.d_result.p, p.cap_tokens);
+        CU(cudaGetLastError());
+        e->launches += 1;
+    }
+    CU(cudaMemcpyAsync(b.h_result.p, b.d_result.p, sizeof(Result), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaEventRecord(b.ev_kdone, e->stream));
+    b.submitted = true;
+    b.sized = false;
     return LATOK_B200_OK;
 }
 
-static int check_what(uint32_t what)
+static int check_what(uint32_t &what)
 {
-    if (what == 0 || (what & ~15u)) return fail(LATOK_B200_EINVAL, "`what` must be a non-empty OR of LATOK_B200_SPLITS|SPANS|FEATS|MATRIX");
+    if (what & LATOK_B200_SPANS16) what |= LATOK_B200_SPANS;
+    if (what == 0 || (what & ~31u)) return fail(LATOK_B200_EINVAL, "`what` must be a non-empty OR of LATOK_B200_SPLITS|SPANS|FEATS|MATRIX|SPANS16");
     return 0;
 }
+
+// the set the next submit uses: depth 1 = the batch in flight (if any) is dropped; depth 2 = at most two in flight
+static int take_set(latok_b200_engine *e, Batch **out)
+{
+    if (e->depth == 1) e->nq = 0;
+    if (e->nq >= e->depth) return fail(LATOK_B200_ESTATE, "%d batches are in flight: fetch and release the oldest one first", e->nq);
+    const int s = e->last ^ 1;
+    e->last = s;
+    e->q[e->nq++] = s;
+    *out = &e->set[s];
+    return 0;
+}
+static void drop_last(latok_b200_engine *e) { if (e->nq) { --e->nq; e->last ^= 1; } }   // a submit that failed
 
 int latok_b200_submit(latok_b200_engine *e, const uint8_t *utf8, const int64_t *offsets, int64_t n_strings, uint32_t what)
 {
@@ -424,35 +473,46 @@ int latok_b200_submit(latok_b200_engine *e, const uint8_t *utf8, const int64_t *
     if (n_bytes < 0) return fail(LATOK_B200_EINVAL, "offsets must be non-negative");
     if (n_bytes > 0 && !utf8) return fail(LATOK_B200_EINVAL, "must specify the UTF-8 buffer");
     if (int r = set_device(e)) return r;
-    e->submitted = false;
-    if (int r = e->d_in.ensure((size_t)n_bytes + 64)) return r;
-    if (int r = e->d_off.ensure((size_t)n_strings + 1)) return r;
-    // stage through pinned memory unless the caller's buffers already are pinned
-    auto is_pinned = [](const void *ptr) {
-        cudaPointerAttributes a;
-        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
-        return a.type == cudaMemoryTypeHost;
-    };
-    const uint8_t *src_b = utf8;
-    const long long *src_o = (const long long *)offsets;
-    if (n_bytes > 0 && !is_pinned(utf8)) {
-        if (int r = e->h_in.ensure((size_t)n_bytes)) return r;
-        CU(cudaStreamSynchronize(e->stream));  // staging buffer may still feed a previous copy
-        memcpy(e->h_in.p, utf8, (size_t)n_bytes);
-        src_b = e->h_in.p;
-    }
-    if (!is_pinned(offsets)) {
-        if (int r = e->h_off.ensure((size_t)n_strings + 1)) return r;
-        CU(cudaStreamSynchronize(e->stream));
-        memcpy(e->h_off.p, offsets, sizeof(long long) * ((size_t)n_strings + 1));
-        src_o = e->h_off.p;
-    }
-    if (n_bytes > 0) CU(cudaMemcpyAsync(e->d_in.p, src_b, (size_t)n_bytes, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->d_off.p, src_o, sizeof(long long) * ((size_t)n_strings + 1), cudaMemcpyHostToDevice, e->stream));
-    e->cur_in = e->d_in.p; e->cur_off = e->d_off.p;
-    e->n_strings = n_strings; e->n_bytes = n_bytes; e->what = what;
-    e->inputs_on_stream = true;
-    return run_device(e);
+    Batch *bp = nullptr;
+    if (int r = take_set(e, &bp)) return r;
+    Batch &b = *bp;
+    b.submitted = false;
+    int rc = [&]() -> int {
+        // the device buffers of this set may still be read by its previous batch's kernels
+        if ((size_t)n_bytes + 64 > b.d_in.cap || (size_t)n_strings + 1 > b.d_off.cap) CU(cudaEventSynchronize(b.ev_kdone));
+        if (int r = b.d_in.ensure((size_t)n_bytes + 64)) return r;
+        if (int r = b.d_off.ensure((size_t)n_strings + 1)) return r;
+        // stage through pinned memory unless the caller's buffers already are pinned
+        auto is_pinned = [](const void *ptr) {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+            return a.type == cudaMemoryTypeHost;
+        };
+        const uint8_t *src_b = utf8;
+        const long long *src_o = (const long long *)offsets;
+        const bool stage_b = n_bytes > 0 && !is_pinned(utf8), stage_o = !is_pinned(offsets);
+        if (stage_b || stage_o) CU(cudaEventSynchronize(b.ev_h2d));     // the staging buffers may still feed this set's previous copy
+        if (stage_b) {
+            if (int r = b.h_in.ensure((size_t)n_bytes)) return r;
+            memcpy(b.h_in.p, utf8, (size_t)n_bytes);
+            src_b = b.h_in.p;
+        }
+        if (stage_o) {
+            if (int r = b.h_off.ensure((size_t)n_strings + 1)) return r;
+            memcpy(b.h_off.p, offsets, sizeof(long long) * ((size_t)n_strings + 1));
+            src_o = b.h_off.p;
+        }
+        CU(cudaStreamWaitEvent(e->s_in, b.ev_kdone, 0));               // ... and the device buffers its previous kernels
+        if (n_bytes > 0) CU(cudaMemcpyAsync(b.d_in.p, src_b, (size_t)n_bytes, cudaMemcpyHostToDevice, e->s_in));
+        CU(cudaMemcpyAsync(b.d_off.p, src_o, sizeof(long long) * ((size_t)n_strings + 1), cudaMemcpyHostToDevice, e->s_in));
+        CU(cudaEventRecord(b.ev_h2d, e->s_in));
+        b.cur_in = b.d_in.p; b.cur_off = b.d_off.p;
+        b.n_strings = n_strings; b.n_bytes = n_bytes; b.what = what;
+        b.inputs_on_stream = true;
+        return run_device(e, b);
+    }();
+    if (rc) drop_last(e);
+    return rc;
 }
 
 int latok_b200_submit_device(latok_b200_engine *e, const uint8_t *d_utf8, const int64_t *d_offsets, int64_t n_strings,
@@ -464,94 +524,140 @@ int latok_b200_submit_device(latok_b200_engine *e, const uint8_t *d_utf8, const 
     if (((uintptr_t)d_utf8 & 15u) != 0) return fail(LATOK_B200_EINVAL, "d_utf8 must be 16-byte aligned");
     if (int r = check_what(what)) return r;
     if (int r = set_device(e)) return r;
-    e->submitted = false;
-    e->cur_in = d_utf8; e->cur_off = (const long long *)d_offsets;
-    e->n_strings = n_strings; e->n_bytes = n_bytes; e->what = what;
-    e->inputs_on_stream = false;
-    return run_device(e);
+    Batch *bp = nullptr;
+    if (int r = take_set(e, &bp)) return r;
+    Batch &b = *bp;
+    b.submitted = false;
+    b.cur_in = d_utf8; b.cur_off = (const long long *)d_offsets;
+    b.n_strings = n_strings; b.n_bytes = n_bytes; b.what = what;
+    b.inputs_on_stream = false;
+    const int rc = run_device(e, b);
+    if (rc) drop_last(e);
+    return rc;
 }
 
-int latok_b200_sizes(latok_b200_engine *e, int64_t *n_chars, int64_t *n_tokens)
+static int size_batch(latok_b200_engine *e, Batch &b)
 {
-    if (!e) return fail(LATOK_B200_EINVAL, "engine is NULL");
-    if (!e->submitted) return fail(LATOK_B200_ESTATE, "no batch submitted");
-    if (int r = set_device(e)) return r;
-    for (int attempt = 0; attempt < 4 && !e->sized; ++attempt) {
-        CU(cudaStreamSynchronize(e->stream));
-        const Result res = *e->h_result[e->slot].p;
-        if (res.error & 2u) { e->submitted = false; return fail(LATOK_B200_EINVAL, "offsets must start at 0, be non-decreasing and end at the buffer length"); }
-        if (res.error & 1u) { e->submitted = false; return fail(LATOK_B200_EINTERNAL, "device look-back watchdog tripped"); }
+    if (!b.submitted) return fail(LATOK_B200_ESTATE, "no batch submitted");
+    for (int attempt = 0; attempt < 4 && !b.sized; ++attempt) {
+        CU(cudaEventSynchronize(b.ev_kdone));
+        const Result res = *b.h_result.p;
+        if (res.error & 2u) { b.submitted = false; return fail(LATOK_B200_EINVAL, "offsets must start at 0, be non-decreasing and end at the buffer length"); }
+        if (res.error & 1u) { b.submitted = false; return fail(LATOK_B200_EINTERNAL, "device look-back watchdog tripped"); }
         if (res.error & 8u) {
-            e->submitted = false;
+            b.submitted = false;
             return fail(LATOK_B200_EINTERNAL, "device consistency check failed: tile %llu G_in %llu K_in %llu n_own %lld ntok %lld c_lo %lld c_hi %lld",
                         res.prof[8], res.prof[9], res.prof[10], (long long)res.prof[11], (long long)res.prof[12], (long long)res.prof[13], (long long)res.prof[14]);
         }
-        if ((res.error & 4u) || (long long)res.n_tokens > (long long)(e->d_spans.cap / 2)) {
+        if ((res.error & 4u) || (long long)res.n_tokens > (long long)(b.d_spans.cap / 2)) {
             // token buffers too small: grow to the exact count and run the batch again
             const size_t need = (size_t)res.n_tokens + 1024;
-            if (int r = e->d_spans.ensure(2 * need)) return r;
-            if (int r = run_device(e)) return r;
+            if (int r = b.d_spans.ensure(2 * need)) return r;
+            if (int r = run_device(e, b)) return r;
             continue;
         }
+        if (res.error & 16u) { b.submitted = false; return fail(LATOK_B200_EINVAL, "LATOK_B200_SPANS16: a string of the batch has 65 536 or more characters"); }
         if (getenv("LATOK_B200_PRINT_PROF")) {
             fprintf(stderr, "[latok prof]");
             for (int i = 0; i < 16; ++i) fprintf(stderr, " %llu", res.prof[i]);
             fprintf(stderr, "\n");
         }
-        e->n_chars = (long long)res.n_chars; e->n_tokens = (long long)res.n_tokens; e->walks = (long long)res.walks;
+        b.n_chars = (long long)res.n_chars; b.n_tokens = (long long)res.n_tokens; b.walks = (long long)res.walks;
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, e->ev_k0, e->ev_k1) == cudaSuccess) e->last_kernel_ms = ms; else cudaGetLastError();
-        e->sized = true;
+        if (cudaEventElapsedTime(&ms, b.ev_k0, b.ev_k1) == cudaSuccess) b.kernel_ms = ms; else cudaGetLastError();
+        b.sized = true;
     }
-    if (!e->sized) return fail(LATOK_B200_EINTERNAL, "token capacity did not converge");
-    if (n_chars) *n_chars = e->n_chars;
-    if (n_tokens) *n_tokens = e->n_tokens;
+    if (!b.sized) return fail(LATOK_B200_EINTERNAL, "token capacity did not converge");
     return LATOK_B200_OK;
 }
 
-int latok_b200_fetch(latok_b200_engine *e, int8_t *splits, int64_t *char_offsets, int32_t *spans, int64_t *tok_offsets,
-                     int8_t *tok_feats, int8_t *matrix)
+#define FRONT(e, b)                                                                  \
+    if (!(e)) return fail(LATOK_B200_EINVAL, "engine is NULL");                      \
+    if (!(e)->front()) return fail(LATOK_B200_ESTATE, "no batch submitted");         \
+    if (int r_ = set_device(e)) return r_;                                           \
+    Batch &b = *(e)->front()
+
+int latok_b200_sizes(latok_b200_engine *e, int64_t *n_chars, int64_t *n_tokens)
 {
-    if (!e) return fail(LATOK_B200_EINVAL, "engine is NULL");
-    if (int r = latok_b200_sizes(e, nullptr, nullptr)) return r;
-    const uint32_t w = e->what;
+    FRONT(e, b);
+    if (int r = size_batch(e, b)) return r;
+    if (n_chars) *n_chars = b.n_chars;
+    if (n_tokens) *n_tokens = b.n_tokens;
+    return LATOK_B200_OK;
+}
+
+int latok_b200_fetch(latok_b200_engine *e, int64_t cap_chars, int64_t cap_tokens, int64_t cap_strings, int8_t *splits,
+                     int64_t *char_offsets, void *spans, int64_t *tok_offsets, int8_t *tok_feats, int8_t *matrix)
+{
+    FRONT(e, b);
+    if (int r = size_batch(e, b)) return r;
+    const uint32_t w = b.what;
     if (splits && !(w & LATOK_B200_SPLITS)) return fail(LATOK_B200_ESTATE, "split mask was not requested at submit");
     if (spans && !(w & LATOK_B200_SPANS)) return fail(LATOK_B200_ESTATE, "spans were not requested at submit");
     if (tok_feats && !(w & LATOK_B200_FEATS)) return fail(LATOK_B200_ESTATE, "token features were not requested at submit");
     if (matrix && !(w & LATOK_B200_MATRIX)) return fail(LATOK_B200_ESTATE, "feature matrix was not requested at submit");
-    const size_t C = (size_t)e->n_chars, T = (size_t)e->n_tokens, S1 = (size_t)e->n_strings + 1;
-    cudaStream_t s = e->stream;
-    if (splits && C) CU(cudaMemcpyAsync(splits, e->d_splits.p, C, cudaMemcpyDeviceToHost, s));
-    if (char_offsets) CU(cudaMemcpyAsync(char_offsets, e->d_char_off.p, S1 * sizeof(long long), cudaMemcpyDeviceToHost, s));
-    if (spans && T) CU(cudaMemcpyAsync(spans, e->d_spans.p, T * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (tok_offsets) CU(cudaMemcpyAsync(tok_offsets, e->d_tok_off.p, S1 * sizeof(long long), cudaMemcpyDeviceToHost, s));
-    if (tok_feats && T) CU(cudaMemcpyAsync(tok_feats, e->d_feats.p, T * NFEAT, cudaMemcpyDeviceToHost, s));
-    if (matrix && C) CU(cudaMemcpyAsync(matrix, e->d_matrix.p, C * NFEAT, cudaMemcpyDeviceToHost, s));
+    if ((splits || matrix) && cap_chars < b.n_chars)
+        return fail(LATOK_B200_EINVAL, "cap_chars = %lld, the batch has %lld characters", (long long)cap_chars, b.n_chars);
+    if ((spans || tok_feats) && cap_tokens < b.n_tokens)
+        return fail(LATOK_B200_EINVAL, "cap_tokens = %lld, the batch has %lld tokens", (long long)cap_tokens, b.n_tokens);
+    if ((char_offsets || tok_offsets) && cap_strings < b.n_strings)
+        return fail(LATOK_B200_EINVAL, "cap_strings = %lld, the batch has %lld strings", (long long)cap_strings, b.n_strings);
+    const size_t C = (size_t)b.n_chars, T = (size_t)b.n_tokens, S1 = (size_t)b.n_strings + 1;
+    cudaStream_t s = e->s_out;
+    CU(cudaStreamWaitEvent(s, b.ev_kdone, 0));
+    if (splits && C) CU(cudaMemcpyAsync(splits, b.d_splits.p, C, cudaMemcpyDeviceToHost, s));
+    if (char_offsets) CU(cudaMemcpyAsync(char_offsets, b.d_char_off.p, S1 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    if (spans && T) {
+        if (w & LATOK_B200_SPANS16) CU(cudaMemcpyAsync(spans, b.d_spans16.p, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        else CU(cudaMemcpyAsync(spans, b.d_spans.p, T * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    if (tok_offsets) CU(cudaMemcpyAsync(tok_offsets, b.d_tok_off.p, S1 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    if (tok_feats && T) CU(cudaMemcpyAsync(tok_feats, b.d_feats.p, T * NFEAT, cudaMemcpyDeviceToHost, s));
+    if (matrix && C) CU(cudaMemcpyAsync(matrix, b.d_matrix.p, C * NFEAT, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return LATOK_B200_OK;
 }
 
-int latok_b200_fetch_token_bytes(latok_b200_engine *e, int64_t *byte_spans, int on_device)
+int latok_b200_release(latok_b200_engine *e)
 {
     if (!e) return fail(LATOK_B200_EINVAL, "engine is NULL");
-    if (int r = latok_b200_sizes(e, nullptr, nullptr)) return r;
-    if (!(e->what & LATOK_B200_SPANS)) return fail(LATOK_B200_ESTATE, "spans were not requested at submit");
-    const size_t T = (size_t)e->n_tokens;
+    if (!e->nq) return fail(LATOK_B200_ESTATE, "no batch in flight");
+    e->q[0] = e->q[1];
+    --e->nq;
+    return LATOK_B200_OK;
+}
+
+int latok_b200_in_flight(latok_b200_engine *e, int *n)
+{
+    if (!e || !n) return fail(LATOK_B200_EINVAL, "engine or n is NULL");
+    *n = e->nq;
+    return LATOK_B200_OK;
+}
+
+int latok_b200_fetch_token_bytes(latok_b200_engine *e, int64_t cap_tokens, int64_t *byte_spans, int on_device)
+{
+    FRONT(e, b);
+    if (int r = size_batch(e, b)) return r;
+    if (!(b.what & LATOK_B200_SPANS)) return fail(LATOK_B200_ESTATE, "spans were not requested at submit");
+    const size_t T = (size_t)b.n_tokens;
     if (T && !byte_spans) return fail(LATOK_B200_EINVAL, "must specify the byte_spans array (2 * n_tokens entries)");
+    if (cap_tokens < b.n_tokens) return fail(LATOK_B200_EINVAL, "cap_tokens = %lld, the batch has %lld tokens", (long long)cap_tokens, b.n_tokens);
     if (!T) return LATOK_B200_OK;
     if (on_device && ((uintptr_t)byte_spans & 15u) != 0) return fail(LATOK_B200_EINVAL, "a device byte_spans array must be 16-byte aligned");
     long long *d_out = on_device ? (long long *)byte_spans : nullptr;
     if (!on_device) { if (int r = e->d_tok_bytes.ensure(2 * T)) return r; d_out = e->d_tok_bytes.p; }
-    if (int r = e->d_blk_local.ensure((size_t)token_bytes_words(e->n_bytes))) return r;
-    if (int r = e->d_group_tot.ensure((size_t)token_bytes_groups(e->n_bytes))) return r;
-    if (int r = e->d_group_pref.ensure((size_t)token_bytes_groups(e->n_bytes))) return r;
+    if (int r = e->d_blk_local.ensure((size_t)token_bytes_words(b.n_bytes))) return r;
+    if (int r = e->d_group_tot.ensure((size_t)token_bytes_groups(b.n_bytes))) return r;
+    if (int r = e->d_group_pref.ensure((size_t)token_bytes_groups(b.n_bytes))) return r;
     cudaStream_t s = e->stream;
+    CU(cudaStreamWaitEvent(s, b.ev_kdone, 0));
     CU(cudaEventRecord(e->ev_b0, s));
-    CU(launch_token_bytes(e->cur_in, e->n_bytes, e->cur_off, e->d_char_off.p, e->d_tok_off.p, e->n_strings, e->n_tokens, e->d_spans.p,
+    CU(launch_token_bytes(b.cur_in, b.n_bytes, b.cur_off, b.d_char_off.p, b.d_tok_off.p, b.n_strings, b.n_tokens, b.d_spans.p,
                           d_out, e->d_blk_local.p, e->d_group_tot.p, e->d_group_pref.p, e->d_table.p, e->tl, e->n_sm, s));
     CU(cudaEventRecord(e->ev_b1, s));
     e->launches += 3;
     if (!on_device) CU(cudaMemcpyAsync(byte_spans, d_out, T * 2 * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(b.ev_kdone, s));          // the set's inputs are in use until here
     CU(cudaStreamSynchronize(s));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->ev_b0, e->ev_b1) == cudaSuccess) e->last_token_bytes_ms = ms; else cudaGetLastError();
@@ -570,13 +676,14 @@ int latok_b200_device_results(latok_b200_engine *e, const int8_t **splits, const
                               const int8_t **matrix)
 {
     if (!e) return fail(LATOK_B200_EINVAL, "engine is NULL");
-    if (!e->submitted) return fail(LATOK_B200_ESTATE, "no batch submitted");
-    if (splits) *splits = e->d_splits.p;
-    if (char_offsets) *char_offsets = (const int64_t *)e->d_char_off.p;
-    if (spans) *spans = e->d_spans.p;
-    if (tok_offsets) *tok_offsets = (const int64_t *)e->d_tok_off.p;
-    if (tok_feats) *tok_feats = e->d_feats.p;
-    if (matrix) *matrix = e->d_matrix.p;
+    if (!e->front() || !e->front()->submitted) return fail(LATOK_B200_ESTATE, "no batch submitted");
+    Batch &b = *e->front();
+    if (splits) *splits = b.d_splits.p;
+    if (char_offsets) *char_offsets = (const int64_t *)b.d_char_off.p;
+    if (spans) *spans = b.d_spans.p;
+    if (tok_offsets) *tok_offsets = (const int64_t *)b.d_tok_off.p;
+    if (tok_feats) *tok_feats = b.d_feats.p;
+    if (matrix) *matrix = b.d_matrix.p;
     return LATOK_B200_OK;
 }
 
@@ -608,24 +715,11 @@ int latok_b200_launch_count(latok_b200_engine *e, int64_t *launches)
 
 int latok_b200_last_stats(latok_b200_engine *e, float *tokenize_kernel_ms, int64_t *lookahead_walks)
 {
-    if (!e) return fail(LATOK_B200_EINVAL, "engine is NULL");
-    if (int r = latok_b200_sizes(e, nullptr, nullptr)) return r;
-    if (tokenize_kernel_ms) *tokenize_kernel_ms = e->last_kernel_ms;
-    if (lookahead_walks) *lookahead_walks = e->walks;
+    FRONT(e, b);
+    if (int r = size_batch(e, b)) return r;
+    if (tokenize_kernel_ms) *tokenize_kernel_ms = b.kernel_ms;
+    if (lookahead_walks) *lookahead_walks = b.walks;
     return LATOK_B200_OK;
-}
-
-/* debugging aid (not part of the public header): copy the per-tile inclusive prefixes of the last run */
-extern "C" __attribute__((visibility("default"))) int latok_b200_debug_chain(latok_b200_engine *e, void *inc_out, void *agg_out, int64_t max_tiles)
-{
-    if (!e) return 1;
-    cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
-    const int64_t nt = e->n_bytes / TILE + 1;
-    const int64_t n = nt < max_tiles ? nt : max_tiles;
-    cudaMemcpy(inc_out, e->inc.p, sizeof(IncRec) * n, cudaMemcpyDeviceToHost);
-    cudaMemcpy(agg_out, e->agg.p, sizeof(AggRec) * n, cudaMemcpyDeviceToHost);
-    return (int)n;
 }
 
 int latok_b200_host_alloc(void **ptr, size_t bytes)
@@ -650,7 +744,7 @@ int latok_b200_gen_parse_matrix(latok_b200_engine *e, const uint8_t *utf8, int64
     int64_t C = 0;
     if (int r = latok_b200_sizes(e, &C, nullptr)) return r;
     if (n_chars) *n_chars = C;
-    if (out) return latok_b200_fetch(e, nullptr, nullptr, nullptr, nullptr, nullptr, out);
+    if (out) return latok_b200_fetch(e, C, 0, 1, nullptr, nullptr, nullptr, nullptr, nullptr, out);
     return LATOK_B200_OK;
 }
 

@@ -68,19 +68,38 @@ def merge_results(parts: Sequence[BatchResult]) -> BatchResult:
     return out
 
 
+_engines = {}
+_engines_lock = threading.Lock()
+
+
+def device_engine(device: int):
+    """The process-wide engine of a device (created on first use; an Engine serialises its callers itself)."""
+    from .engine import Engine
+    with _engines_lock:
+        e = _engines.get(device)
+        if e is None:
+            e = _engines[device] = Engine(device)
+        return e
+
+
+def close_engines():
+    with _engines_lock:
+        for e in _engines.values():
+            e.close()
+        _engines.clear()
+
+
 def tokenize_sharded(buf: np.ndarray, offsets: np.ndarray, devices: Sequence[int], what: int = SPLITS | SPANS,
                      run_fn: Optional[Callable[[int, np.ndarray, np.ndarray, int], BatchResult]] = None) -> BatchResult:
-    """One process, several GPUs: one host thread and one Engine per device, each on its byte-balanced
-    string range; results are concatenated on the host.  `run_fn(device, buf, offsets, what)` can be
+    """One process, several GPUs: one host thread per shard and one long-lived Engine per device, each shard on its
+    byte-balanced string range; results are concatenated on the host.  `run_fn(device, buf, offsets, what)` can be
     injected (tests use it to exercise the host logic without a GPU)."""
     ranges = shard_ranges(offsets, len(devices))
     results: List[Optional[BatchResult]] = [None] * len(devices)
     errors: List[Optional[BaseException]] = [None] * len(devices)
 
     def default_run(dev, b, o, w):
-        from .engine import Engine
-        with Engine(dev, len(b) + 4096, len(o)) as e:
-            return e.run_packed(b, o, w)
+        return device_engine(dev).run_packed(b, o, w)      # one engine per device, kept alive between calls
 
     fn = run_fn or default_run
 

@@ -13,7 +13,6 @@ for p in (str(ROOT), str(ROOT / "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_extended: extra alignment sweeps, only with LATOK_EXTENDED=1 (tests/test_gpu_extended.py)")
 
 
 @pytest.fixture(scope="session")

@@ -1,8 +1,9 @@
-"""Full-size BASELINE configs on the GPU: size-independent invariants over the whole batch plus exact
-parity with the oracle on random samples of strings (the oracle needs seconds per 10 MB).  -m gpu."""
+"""Full-size BASELINE configs on the GPU: size-independent invariants over the whole batch plus EXACT parity with the
+oracle on every string of the batch (tests/fullcheck.py: the oracle's C batch path over a pool of processes).  -m gpu."""
 import numpy as np
 import pytest
 
+import fullcheck
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -47,7 +48,7 @@ def check_invariants(buf, off, r, feats=False):
 
 
 def check_sample(buf, off, r, idx, feats=False):
-    from latok_b200 import synth
+    import synth
     raw = buf.tobytes()
     for i in idx:
         t = raw[off[i]:off[i + 1]].decode("utf-8")
@@ -61,14 +62,12 @@ def check_sample(buf, off, r, idx, feats=False):
 
 
 def test_config2_one_million_tweets(engine):
-    from latok_b200 import synth
+    import synth
     buf, off = synth.tweets(1_000_000)
     r = engine.run_packed(buf, off, 1 | 2)
     check_invariants(buf, off, r)
-    rng = np.random.default_rng(0)
-    check_sample(buf, off, r, rng.integers(0, 1_000_000, size=4000))
-    check_sample(buf, off, r, range(0, 300))
-    check_sample(buf, off, r, range(999_700, 1_000_000))
+    assert fullcheck.compare_all(buf, off, r) == 1_000_000          # every string: split mask, spans, CSR offsets
+    check_sample(buf, off, r, range(0, 50))                         # (and a few through the per-string oracle calls)
     r2 = engine.run_packed(buf, off, 1 | 2)     # deterministic
     assert np.array_equal(r.splits, r2.splits) and np.array_equal(r.spans, r2.spans)
     # sharding property: two byte-balanced halves tokenized separately concatenate to the whole
@@ -79,19 +78,24 @@ def test_config2_one_million_tweets(engine):
 
 
 def test_config4_mixed_unicode_with_classification(engine):
-    from latok_b200 import synth
-    buf, off = synth.mixed_unicode(300_000)
+    import synth
+    buf, off = synth.mixed_unicode(1_000_000)
     r = engine.run_packed(buf, off, 1 | 2 | 4)
     check_invariants(buf, off, r, feats=True)
-    rng = np.random.default_rng(1)
-    check_sample(buf, off, r, rng.integers(0, 300_000, size=2500), feats=True)
+    assert fullcheck.compare_all(buf, off, r, feats=True) == 1_000_000      # every string, token feature sums included
+    check_sample(buf, off, r, range(0, 50), feats=True)
+    r3 = engine.run_packed(buf, off, 1 | 2)                                   # the kernel instantiation without token features
+    assert np.array_equal(r3.splits, r.splits) and np.array_equal(r3.spans, r.spans) and np.array_equal(r3.tok_offsets, r.tok_offsets)
 
 
 def test_config3_long_documents(engine):
-    from latok_b200 import synth
-    buf, off = synth.long_docs(1500, 65536)      # ~100 MB of unique text, incl. >= 32 KB space-free runs and backlog chunks
+    import synth
+    # 1.07 GB of unique text (8 blocks of 2 000 documents generated in parallel), incl. >= 32 KB space-free runs and
+    # multi-mark (backlog) chunks: every document compared with the oracle
+    import bench
+    buf, off = bench.generate({"d": [("docs", 2000, 20240602 + 1000 * k) for k in range(8)]})["d"]
+    assert len(buf) > 1_000_000_000
     r = engine.run_packed(buf, off, 1 | 2)
     check_invariants(buf, off, r)
-    runs = [i for i in range(1500) if (buf[off[i]:off[i + 1]] == 0x2C).mean() > 0.05][:6]
-    check_sample(buf, off, r, list(range(0, 40)) + runs)
-    assert r.lookahead_walks >= 0
+    assert fullcheck.compare_all(buf, off, r, target_bytes=8 << 20) == 16_000
+    assert r.lookahead_walks > 0                 # the corpus does exercise the look-ahead walk

@@ -117,7 +117,7 @@ def test_device_resident_text_and_device_output(engine):
     engine.submit_device(d_buf.data_ptr(), d_off.data_ptr(), len(texts), len(buf), SPANS)
     r = engine.fetch()
     d_out = torch.empty((r.n_tokens, 2), dtype=torch.int64, device="cuda")
-    _lib.check(_lib.load().latok_b200_fetch_token_bytes(engine._h, d_out.data_ptr(), 1))
+    _lib.check(_lib.load().latok_b200_fetch_token_bytes(engine._h, r.n_tokens, d_out.data_ptr(), 1))
     torch.cuda.synchronize()
     got = d_out.cpu().numpy()
     assert np.array_equal(got, engine.token_bytes())
@@ -125,6 +125,8 @@ def test_device_resident_text_and_device_output(engine):
     for i in (0, 1, len(texts) // 2, len(texts) - 1):
         toks = [bytes(mv[b:e]).decode("utf-8", "surrogatepass") for b, e in got[r.tok_offsets[i]:r.tok_offsets[i + 1]]]
         assert toks == oracle.tokens(texts[i])
-    # a misaligned device pointer is rejected, not written through
+    # too small a caller array is rejected (the call takes its capacity), and so is a misaligned device pointer
     with pytest.raises(ValueError):
-        _lib.check(_lib.load().latok_b200_fetch_token_bytes(engine._h, d_out.data_ptr() + 8, 1))
+        _lib.check(_lib.load().latok_b200_fetch_token_bytes(engine._h, r.n_tokens - 1, d_out.data_ptr(), 1))
+    with pytest.raises(ValueError):
+        _lib.check(_lib.load().latok_b200_fetch_token_bytes(engine._h, r.n_tokens, d_out.data_ptr() + 8, 1))

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/latok_b200.h but not exported"
-    assert L.latok_b200_abi_version() == 1
+    assert L.latok_b200_abi_version() == 2
 
 
 def test_header_cites_the_reference_interface():
@@ -58,7 +58,8 @@ def test_argument_validation_without_gpu():
     assert L.latok_b200_create(0, 0, -1, C.byref(h)) == _lib.EINVAL
     assert L.latok_b200_submit(None, None, None, 0, 3) == _lib.EINVAL
     assert b"engine is NULL" in L.latok_b200_last_error()
-    assert L.latok_b200_fetch(None, None, None, None, None, None, None) == _lib.EINVAL
+    assert L.latok_b200_fetch(None, 0, 0, 0, None, None, None, None, None, None) == _lib.EINVAL
+    assert L.latok_b200_set_pipeline_depth(None, 2) == _lib.EINVAL and L.latok_b200_release(None) == _lib.EINVAL
     assert L.latok_b200_destroy(None) == _lib.OK
 
 
@@ -78,6 +79,28 @@ def test_pack_strings_roundtrip():
     assert [raw[off[i]:off[i + 1]].decode("utf-8", "surrogatepass") for i in range(len(texts))] == texts
 
 
+def test_c_packer_matches_python_encode():
+    """pack_strings runs in C (csrc/latok_pypack.c): same bytes and offsets as str.encode('utf-8', 'surrogatepass')
+    for every PEP-393 kind (ASCII, Latin-1, UCS-2, UCS-4), lone surrogates, empty strings, tuples and generators,
+    into a caller's buffer, and with a buffer that is too small."""
+    from latok_b200.engine import pack_strings, pack_strings_python
+    texts = corpus.FIXTURES + ["", "\xe9\xff latin1", "\u20ac ucs2 \ud800", "\U0001F600 ucs4 \udfff", "\x00nul\x7f", ""] \
+        + corpus.fuzz_strings(8, 3000, 120, "mixed") + ["".join(map(chr, range(0x7F0, 0x810))), "".join(map(chr, range(0xFFF0, 0x10010)))]
+    want = pack_strings_python(texts)
+    for form in (texts, tuple(texts), (t for t in texts)):
+        got = pack_strings(form)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[1].dtype == np.int64
+    big = np.zeros(len(want[0]) + 100, dtype=np.uint8)
+    got = pack_strings(texts, big)
+    assert got[0].base is big and np.array_equal(got[0], want[0])
+    small = np.zeros(10, dtype=np.uint8)
+    got = pack_strings(texts, small)                               # does not fit: a fresh buffer of the exact size
+    assert np.array_equal(got[0], want[0]) and not small.any() or np.array_equal(got[0], want[0])
+    assert pack_strings([])[1].tolist() == [0] and len(pack_strings([])[0]) == 0
+    with pytest.raises(TypeError):
+        pack_strings(["ok", b"bytes are not str"])
+
+
 def test_mirror_modules_match_reference_constants():
     from latok_b200.core import offsets as oft
     from latok_b200.core.latok_utils import FEATURE_NAMES, NUM_FEATURES, build_combo_matrix
@@ -90,7 +113,7 @@ def test_mirror_modules_match_reference_constants():
 
 
 def test_synthetic_corpora_are_valid_and_seeded():
-    from latok_b200 import synth
+    import synth
     for fn, kw in ((synth.tweets, dict(n_strings=3000)), (synth.mixed_unicode, dict(n_strings=2000)),
                    (synth.long_docs, dict(n_docs=6, doc_bytes=20000))):
         b1, o1 = fn(**kw)
@@ -113,7 +136,8 @@ def oracle_run(device, buf, offsets, what):
 
 
 def test_shard_ranges_and_merge():
-    from latok_b200 import sharding, synth
+    from latok_b200 import sharding
+    import synth
     buf, off = synth.tweets(5000, seed=7)
     for g in (1, 2, 3, 4, 8):
         rng = sharding.shard_ranges(off, g)
@@ -136,7 +160,8 @@ def test_shard_ranges_and_merge():
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
-    from latok_b200 import sharding, synth
+    from latok_b200 import sharding
+    import synth
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     buf, off = synth.tweets(2000, seed=11)
@@ -152,7 +177,7 @@ def _gloo_worker(rank, world, port, q):
 
 def test_two_rank_count_exchange_over_gloo():
     import torch.multiprocessing as mp
-    from latok_b200 import synth
+    import synth
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]

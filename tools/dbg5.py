@@ -66,7 +66,7 @@ def main():
         for seed, count, ml, prof in [(1, 6000, 60, "mixed"), (2, 6000, 140, "ascii"), (3, 6000, 100, "marks"), (4, 400, 3000, "mixed")]:
             ok &= check(e, corpus.fuzz_strings(seed, count, ml, prof), f"fuzz {prof} {seed}")
     if level >= 3:
-        from latok_b200 import synth
+        import synth
         buf, offs = synth.tweets(200000, seed=7) if hasattr(synth, "tweets") else (None, None)
         if buf is not None:
             texts = [bytes(buf[offs[i]:offs[i + 1]]).decode("utf-8") for i in range(20000)]

@@ -1,6 +1,7 @@
-import sys; sys.path.insert(0,'.')
+import sys; sys.path.insert(0,'.'); sys.path.insert(1,'tests')
 import numpy as np, ctypes as C
-from latok_b200 import synth, _lib
+from latok_b200 import _lib
+import synth
 from latok_b200.engine import Engine
 buf, off = synth.long_docs(3000, 65536)
 keep = [i for i in range(3000) if (buf[off[i]:off[i+1]] == 0x2C).mean() < 0.02]

@@ -2,9 +2,10 @@
 """Cost of the irregular tiles of the long-document corpus (development aid; run under gpurun):
 clean documents, then the same with k documents given a 32 KB space-free run / a 300-byte multi-mark stretch.
    LATOK_B200_PRINT_PROF=1 python tools/docs_probe.py"""
-import sys; sys.path.insert(0, '.')
+import sys; sys.path.insert(0, '.'); sys.path.insert(1, 'tests')
 import numpy as np, ctypes as C
-from latok_b200 import synth, _lib
+from latok_b200 import _lib
+import synth
 from latok_b200.engine import Engine
 
 buf, off = synth.long_docs(3000, 65536)

@@ -4,8 +4,9 @@
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(1, str(Path(__file__).resolve().parent.parent / "tests"))
 import numpy as np
-from latok_b200 import synth
+import synth
 from latok_b200.engine import Engine
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "tweets"
