@@ -92,7 +92,8 @@ LATOK_B200_API int latok_b200_set_rules(latok_b200_engine *e,
  * one and latok_b200_release() retires it.  The loop
  *     submit(0); for i: { submit(i+1); fetch(i); release(); }
  * on ONE host thread overlaps the host -> device copy and the kernels of batch i+1 with the device -> host copy of
- * batch i (separate copy-in, compute and copy-out streams; this is the double buffering of the north star). */
+ * batch i (separate copy-in, compute and copy-out streams; this is the double buffering of the north star).
+ * Changing the depth drops the batches in flight. */
 LATOK_B200_API int latok_b200_set_pipeline_depth(latok_b200_engine *e, int depth);
 /* Host buffers in: stages pageable memory through the set's pinned buffers (pinned caller memory, e.g. from
  * latok_b200_host_alloc, goes straight to the device), cudaMemcpyAsync on the copy-in stream, kernels on the compute

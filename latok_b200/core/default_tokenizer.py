@@ -90,8 +90,13 @@ def _token_texts(text: str, spans: np.ndarray) -> List[str]:
 
 
 def tokenize_batch(texts: Sequence[str], engine=None) -> List[List[str]]:
+    """[list(tokenize(t)) for t in texts]: one kernel pass, then the token strings cut by one C loop
+    (`text[s:e].strip()`, dropped when empty, default_tokenizer.py:151-158)."""
+    from .. import _pack
+    if not isinstance(texts, (list, tuple)):
+        texts = list(texts)
     r = batch_arrays(texts, splits=False, spans=True, engine=engine)
-    return [_token_texts(t, r.string_spans(i)) for i, t in enumerate(texts)]
+    return _pack.slice_tokens(texts, r.spans, r.tok_offsets)
 
 
 class PackedTokens:

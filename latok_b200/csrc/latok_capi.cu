@@ -325,7 +325,7 @@ int latok_b200_set_pipeline_depth(latok_b200_engine *e, int depth)
 {
     if (!e) return fail(LATOK_B200_EINVAL, "engine is NULL");
     if (depth != 1 && depth != 2) return fail(LATOK_B200_EINVAL, "pipeline depth must be 1 or 2");
-    if (e->nq > 1) return fail(LATOK_B200_ESTATE, "two batches are in flight; release them before changing the pipeline depth");
+    e->nq = 0;                   // batches in flight are dropped (their device work still completes)
     e->depth = depth;
     return LATOK_B200_OK;
 }

@@ -125,6 +125,7 @@ class Engine:
         with self._lock:
             _lib.check(self._L.latok_b200_set_pipeline_depth(self._h, depth))
             self._depth = depth
+            self._flight = []            # (the library drops the batches in flight)
 
     def _push(self, rec):
         if self._depth == 1:
@@ -231,7 +232,6 @@ class Engine:
             if self._flight and self._depth == 2:
                 raise RuntimeError("batches are in flight")
             self.set_pipeline_depth(2)
-            self._flight = []
             try:
                 pending = 0
                 for buf, offsets in batches:

@@ -101,6 +101,23 @@ def test_c_packer_matches_python_encode():
         pack_strings(["ok", b"bytes are not str"])
 
 
+def test_c_token_slicing_matches_the_reference_loop():
+    """_pack.slice_tokens (the C loop behind tokenize_batch) = the reference's `text[s:e].strip()`, dropped when empty
+    (default_tokenizer.py:151-158), on the oracle's spans, for int32 and uint16 span arrays."""
+    from latok_b200 import _pack
+    from oracle import oracle
+    texts = [t for t in corpus.FIXTURES + corpus.fuzz_strings(2, 1500, 100, "mixed") if t]
+    o = oracle.tokenize_batch(texts, feats=False)
+    want = [[tok for tok in (t[s:e].strip() for s, e in o["spans"][o["tok_offsets"][i]:o["tok_offsets"][i + 1]]) if tok]
+            for i, t in enumerate(texts)]
+    assert want == [oracle.tokens(t) for t in texts]
+    assert _pack.slice_tokens(texts, o["spans"], o["tok_offsets"]) == want
+    assert _pack.slice_tokens(texts, o["spans"].astype(np.uint16), o["tok_offsets"]) == want
+    bad = o["spans"].copy(); bad[0, 1] = 10 ** 6
+    with pytest.raises(ValueError):
+        _pack.slice_tokens(texts, bad, o["tok_offsets"])
+
+
 def test_mirror_modules_match_reference_constants():
     from latok_b200.core import offsets as oft
     from latok_b200.core.latok_utils import FEATURE_NAMES, NUM_FEATURES, build_combo_matrix
