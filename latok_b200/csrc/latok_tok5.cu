@@ -13,16 +13,19 @@
 //           byte -> bit-plane transpose, bit-sliced ASCII classification, class-table patch for multi-byte
 //           characters, squeeze to character space, prev/next/after-next context (latok.c:68-73,99-134), rule
 //           sums (latok.c:318-341), and the block mask's forward half as a carry-propagating add
-//           (latok.c:218-244 when no chunk holds two marks; otherwise the whole tile is re-done by the exact
-//           mark-by-mark evaluation, pass B)
+//           (latok.c:218-244 when no chunk holds two marks; a step that does is evaluated mark by mark)
 //   pass C  backward over the steps: blank the chunks whose closer is hot, split values
 //           (default_tokenizer.py:121-132), token flags (default_tokenizer.py:148-158), counts
 //   -> the service warp sums the ranges of the tile, publishes the aggregate, looks back, hands the prefix down
 //   pass D  forward: split bytes and (start,end) pairs staged per step in shared memory and written with
 //           aligned 16-byte stores; CSR offsets by one lane per string.
-// Rare paths: a backlog left by a range's last chunk (several marks) is handed to the next range, which repeats its
-// ordinary analysis with it (mode 2, settle()); a range that does not begin / end at a chunk closer (space-free run
-// longer than the search windows) sends its tile through the exact evaluation (mode 1, pass B + look-ahead walk).
+// Rare paths, one mechanism (resolve()): every range posts, with its counts, how it transforms a block-mask backlog
+// (x -> max(x + u, f0): u = marks - closers, f0 = what it leaves when nothing enters), the marks in front of its first
+// closer and whether it begins / ends at a chunk closer.  The service warp composes these over the ranges of the tile:
+// the backlog that really enters every range (several marks in a chunk, a backlog from the previous tile) and, for a
+// range that ends inside a chunk (a space-free run longer than the search windows), whether that chunk's closer will be
+// hot (a pending mark, a mark in a later range, or -- past the end of the tile -- the look-ahead walk).  The ranges whose
+// (backlog, hot tail) differ from what they assumed (0, 0) repeat their ORDINARY analysis with them, all at once.
 // The warps run one tile ahead of the look-back: analysis of tile k+1, then pass D of tile k, whose state waits in
 // place of its input bytes (two window buffers per warp).  Tickets are taken by the first warp that is ready for the
 // next tile, so ticket order follows start order and predecessors publish first.
@@ -52,18 +55,16 @@ enum { BAR_AGG = 1, BAR_PRE = 3 };
 static_assert(RANGE == WIN - HALO && HALO % 32 == 0 && RANGE % 16 == 0, "geometry");
 static_assert(TSTAGE >= STEP + 64, "the token stage doubles as the byte stage of partly owned split-mask chunks");
 
-struct WAgg { int n_own, ntok, lft, v, flags, pad[3]; };
-struct Slot { unsigned long long G, K, base; int mode, x_in; };
+struct WAgg { int n_own, ntok, lft, v, flags, u, mb1, pad; };   // flags: 1 have, 2 closed, 4 lo_found, 8 holds a closer
+struct Slot { unsigned long long G, K, base; int mode, pad; };
 struct RInfo { int c_lo, c_hi, n_own, ntok, flags, pad[3]; };    // flags: 1 have, 2 closed, 4 lo_found, 8 last_range
 struct Ctl {
     int tile_id[2], tk_cnt[2], tk_flag[2];
-    int xr[2];                           // exact evaluation: the round for which slot[].x_in (the backlog entering the tile) is valid
-    int pad0[2];
-    int patch_x[NW];                     // mode 2: backlog with which a range repeats its (regular) analysis, -1: not this range
+    int pad0[4];
+    int patch_x[NW];                     // mode 2: backlog with which a range repeats its analysis, -1: not this range
+    int patch_far[NW];                   // ... and whether the chunk open at its end will be closed hot
     Slot slot[2];
     WAgg wagg[2][NW];
-    int xfu[NW], xfv[NW];                // exact evaluation: backlog transfer function of every range of the tile
-    unsigned xfgen[NW];
     RInfo rinfo[NW][2];
     int tokstep[NW][2][RS];              // tokens per step
     int nsa[NW][2][RS];                  // first split after the step (range-relative character index, -1: none)
@@ -99,15 +100,6 @@ __host__ __device__ inline Plan plan(const TableLayout &tl, bool is_default)
 #define PROF5(i) do { if (lane == 0) { long long _t = clock64(); atomicAdd(&p.result->prof[i], (unsigned long long)(_t - _prof_t)); _prof_t = _t; } } while (0)
 #else
 #define PROF5(i) do { } while (0)
-#endif
-
-// LATOK_PROFX builds: where the time of the EXACT evaluation goes (summed clock64() deltas of every compute warp):
-// prof[0] string map + pass A, [1] transfer functions, [2] wait for the backlog, [3] mark-by-mark pass, [4] look-ahead
-// walk, [5] pass C, [6] window reload, [7] number of exact range evaluations
-#ifdef LATOK_PROFX
-#define PROFX(i) do { if (exact && lane == 0) { long long _t = clock64(); atomicAdd(&p.result->prof[i], (unsigned long long)(_t - _px)); _px = _t; } } while (0)
-#else
-#define PROFX(i) do { } while (0)
 #endif
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -148,25 +140,35 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         for (int i = threadIdx.x; i < n16; i += NTH) reinterpret_cast<uint4 *>(tableS)[i] = __ldg(src + i);
         if (threadIdx.x == 0) {
             for (int w = 0; w < 2 * NW; ++w) mbar_init(mbar + w, 1);
-            for (int w = 0; w < NW; ++w) { ctl.xfu[w] = 0; ctl.xfv[w] = 0; ctl.xfgen[w] = 0; }
-            for (int b = 0; b < 2; ++b) { ctl.tile_id[b] = 0; ctl.tk_cnt[b] = 0; ctl.tk_flag[b] = 0; ctl.xr[b] = 0; }
+            for (int b = 0; b < 2; ++b) { ctl.tile_id[b] = 0; ctl.tk_cnt[b] = 0; ctl.tk_flag[b] = 0; }
         }
     }
     __syncthreads();
     const bool want_spans = (p.what & 2u) != 0u, want_splits = (p.what & 1u) != 0u;
     const int ntiles_i = (int)p.ntiles;
 
+    Tables tb;
+    tb.ascii_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.ascii_feat - p.tl.lutv));
+    tb.class_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.class_feat - p.tl.lutv));
+    tb.stage1 = reinterpret_cast<const latok_stage1_t *>(tableS + (p.tl.stage1 - p.tl.lutv));
+    tb.stage2 = p.table_blob + p.tl.stage2;
+    tb.low_limit = p.tl.low_limit; tb.high_first = p.tl.high_first; tb.high_last = p.tl.high_last; tb.high_feat = p.tl.high_feat;
+
     // =================================================================================================
-    // service warp: tile aggregate, look-back, prefix hand-down
+    // service warp: tile aggregate, backlog / hot-tail resolution, look-back, prefix hand-down
     // =================================================================================================
     if (warp == 0) {
-        unsigned round = 0;
         for (int k = 0;; ++k) {
             const int s = k & 1;
-            int n = 0, ntok = 0, lft_rel = -1, v = 0; bool irregular = false;
-            int v_range = 0;             // lane i: backlog that range i hands to the next one
-            int x_used = 0;              // lane i: backlog with which range i has been analysed
-            auto gather = [&]() {
+            int n = 0, ntok = 0, lft_rel = -1;
+            // lane i < NW: what range i posted with its FIRST analysis (nothing entering, tail not hot): backlog left (sf0),
+            // flags, and -- only for ranges that begin inside a chunk (flag 4 clear) -- marks - closers (su; NEG: a string
+            // boundary resets the backlog) and the marks in front of the first closer (smb1) ...
+            int su = 0, sf0 = 0, smb1 = 0, sflags = 2 | 4;
+            // ... what it has been analysed with so far, and the backlog it left the last time
+            int x_used = 0, far_used = 0, v_last = 0;
+            bool again = false;                                  // this range took part in the round just gathered
+            auto gather = [&](bool first) {
                 nb_sync(BAR_AGG + s, NTH);
                 const WAgg a = ctl.wagg[s][lane < NW ? lane : 0];
                 const int mn = lane < NW ? a.n_own : 0, mk = lane < NW ? a.ntok : 0;
@@ -179,89 +181,98 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 const int src = hl ? 31 - __clz(hl) : 0;
                 const int lv = __shfl_sync(FULL, pn - mn + a.lft, src);
                 lft_rel = hl ? lv : -1;
-                v = __shfl_sync(FULL, a.v, NW - 1);
-                v_range = lane < NW ? a.v : 0;
-                irregular = __any_sync(FULL, lane < NW && (a.flags & 1));
+                if (first && lane < NW) { su = a.u; sf0 = a.v; smb1 = a.mb1; sflags = a.flags; v_last = a.v; }
+                if (!first && again) v_last = a.v;
             };
-            // Regular tile (every range begins and ends at a chunk closer): a range that ends in a chunk with several marks
-            // hands a backlog to the next range, which then repeats its ordinary analysis with that backlog entering
-            // (mode 2; nothing else of the tile is touched).  Repeats until every range has seen the backlog its
-            // predecessor really leaves; `x_tile` = backlog entering the tile.
-            auto settle = [&](int x_tile) {
+            // Backlog entering / hot tail of every range, given the backlog `x_tile` that enters the tile; ranges that were
+            // analysed with something else repeat their analysis (mode 2), all at once.  Returns the backlog leaving the tile.
+            // A range that begins at a chunk closer has no summary: if a backlog enters it after all, what it leaves is known
+            // once it has repeated its analysis, and the ranges behind it follow in the next round (rare, short cascades).
+            auto resolve = [&](int x_tile) -> int {
+                // nothing enters, nothing is left, every range ends at a closer: almost every tile
+                if (x_tile == 0 && !__any_sync(FULL, lane < NW && (sflags & 1) != 0 && (sf0 != 0 || (sflags & 2) == 0 || x_used != 0 || far_used != 0)))
+                    return 0;
+                int x_out = x_tile;
                 for (;;) {
-                    int want = __shfl_up_sync(FULL, v_range, 1);
-                    if (lane == 0) want = x_tile;
-                    const bool need = lane < NW && want != x_used;
-                    if (!__any_sync(FULL, need)) break;
-                    if (lane < NW) st_vs32(&ctl.patch_x[lane], need ? want : -1);
-                    if (need) x_used = want;
+                    int xin = x_tile, x = x_tile, xend = 0;
+                    bool known = true, kin = false, kend = false;    // (x known: entering range i / at its end)
+#pragma unroll 1
+                    for (int i = 0; i < NW; ++i) {
+                        const int ui = __shfl_sync(FULL, su, i), fi = __shfl_sync(FULL, sf0, i), fl = __shfl_sync(FULL, sflags, i);
+                        const int xu = __shfl_sync(FULL, x_used, i), vl = __shfl_sync(FULL, v_last, i);
+                        if (lane == i) { xin = x; kin = known; }
+                        if (known) {
+                            if ((fl & 1) == 0) { /* no data: passes the backlog on */ }
+                            else if ((fl & 4) == 0) x = max(x + ui, fi);
+                            else if (x == 0) x = fi;
+                            else if (x == xu) x = vl;                 // it has been analysed with exactly this backlog
+                            else known = false;
+                        }
+                        if (lane == i) { xend = x; kend = known; }
+                    }
+                    x_out = x;
+                    const bool all_known = known;
+                    const bool have = lane < NW && (sflags & 1) != 0;
+                    const bool open = have && (sflags & 2) == 0;           // the range ends inside a chunk
+                    int far = far_used;
+                    bool walk = false;
+                    {
+                        const unsigned Bm = __ballot_sync(FULL, lane < NW && smb1 > 0), Bc = __ballot_sync(FULL, lane < NW && (sflags & 8) != 0);
+                        const unsigned Bn = __ballot_sync(FULL, lane < NW && (sflags & 1) == 0);
+                        if (open && kend) {
+                            far = 0;
+                            if (xend > 0) far = 1;
+                            else {
+                                // the first later range that holds a mark in front of its first closer / a closer / no data
+                                const unsigned dec = (Bm | Bc | Bn) & (0xFFFFFFFEu << lane) & mask_lt(NW);
+                                if (dec) far = (int)((Bm >> (__ffs(dec) - 1)) & 1u);
+                                else walk = true;                            // the chunk runs on past the end of the tile
+                            }
+                        }
+                    }
+                    if (__any_sync(FULL, walk)) {
+                        const long long tile_w = ld_vs32(&ctl.tile_id[s]);
+                        const bool any = walk_ahead(p, tb, (tile_w + 1) * (long long)NW * RANGE, lane);
+                        if (walk) far = any ? 1 : 0;
+                        if (lane == 0) atomicAdd(&p.result->walks, 1ull);
+                    }
+                    const bool need = have && kin && (xin != x_used || far != far_used);
+                    if (!__any_sync(FULL, need)) {
+                        if (!all_known && lane == 0) atomicOr(&p.result->error, 1u);      // (cannot happen: every round makes a range known)
+                        break;
+                    }
+                    if (lane < NW) { st_vs32(&ctl.patch_x[lane], need ? xin : -1); st_vs32(&ctl.patch_far[lane], far); }
+                    if (need) { x_used = xin; far_used = far; }
+                    again = need;
                     if (lane == 0) { ctl.slot[s].mode = 2; atomicAdd(&p.result->prof[15], 1ull); }
                     __threadfence_block();
                     __syncwarp();
                     nb_arrive(BAR_PRE + s, NTH);
-                    gather();
+                    gather(false);
                 }
+                return x_out;
             };
-            // the compute warps are told to run the exact evaluation; the backlog that enters the tile may follow later
-            // (give_backlog): reload, pass A and the ranges' transfer functions do not need it
-            auto give_backlog = [&](int x_in) {
-                if (lane == 0) {
-                    st_vs32(&ctl.slot[s].x_in, x_in);
-                    __threadfence_block();
-                    st_vs32(&ctl.xr[s], (int)round);
-                }
-                __syncwarp();
-            };
-            auto order_exact = [&](int x_in, bool known) {
-                ++round;
-                if (lane == 0) {
-                    ctl.slot[s].mode = 1;
-                    __threadfence_block();
-                }
-                __syncwarp();
-                if (known) give_backlog(x_in);
-                nb_arrive(BAR_PRE + s, NTH);
-            };
-            gather();
+            gather(true);
             const long long tile = ld_vs32(&ctl.tile_id[s]);
             if (tile >= p.ntiles) break;
-            Prefix pre;
-            if (irregular) {
-                // the fast evaluation does not apply (a chunk with several marks, or one that is open at a range boundary):
-                // the warps start the exact evaluation at once (windows, pass A, transfer functions) while the exact prefix
-                // is taken; the mark-by-mark pass then runs with the backlog that really enters.  Nothing is published for
-                // this tile until then, so the tiles after it wait
-#ifdef LATOK_PROFILE
-                const long long _s0 = clock64();
-#endif
-                order_exact(0, false);
-                pre = lookback(tile, p, lane);
+            // the aggregate is published under the assumption that no backlog enters the tile (true for almost every tile)
+            int v = resolve(0);
+            if (lane == 0) {
+                uint4 r;
+                r.x = (p.epoch << 2) | 1u;
+                r.y = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
+                r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
+                st_rec(p.agg + tile, r);
+            }
+            const Prefix pre = lookback(tile, p, lane);
+            if (pre.x != 0) {
 #ifdef LATOK_PROFILE
                 const long long _s1 = clock64();
 #endif
-                give_backlog(pre.x); gather();
+                v = resolve(pre.x);
 #ifdef LATOK_PROFILE
-                if (lane == 0) { atomicAdd(&p.result->prof[9], (unsigned long long)(_s1 - _s0)); atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
+                if (lane == 0) { atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
 #endif
-                if (lane == 0) atomicAdd(&p.result->prof[15], 1ull);
-            } else {
-                settle(0);
-                const unsigned ylf = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
-                if (lane == 0) {
-                    uint4 r;
-                    r.x = (p.epoch << 2) | 1u; r.y = ylf; r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
-                    st_rec(p.agg + tile, r);
-                }
-                pre = lookback(tile, p, lane);
-                if (pre.x != 0) {
-#ifdef LATOK_PROFILE
-                    const long long _s1 = clock64();
-#endif
-                    settle(pre.x);
-#ifdef LATOK_PROFILE
-                    if (lane == 0) { atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
-#endif
-                }
             }
             if (lane == 0) {
                 IncRec *ir = p.inc + tile;
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
                 st_rec(p.agg + tile, r);
                 Slot &sl = ctl.slot[s];
-                sl.G = pre.G; sl.K = pre.K; sl.base = pre.base; sl.mode = 0; sl.x_in = 0;
+                sl.G = pre.G; sl.K = pre.K; sl.base = pre.base; sl.mode = 0;
                 __threadfence_block();
             }
             __syncwarp();
@@ -296,12 +307,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     auto Xof = [&](int b) -> uint8_t * { return wbase + (sp.x[b] - sp.warp0); };
     uint32_t *sbmS = reinterpret_cast<uint32_t *>(wbase + (sp.sbm - sp.warp0));
     auto tempof = [&](int b) -> uint32_t * { return reinterpret_cast<uint32_t *>(wbase + (sp.temp[b] - sp.warp0)); };
-    Tables tb;
-    tb.ascii_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.ascii_feat - p.tl.lutv));
-    tb.class_feat = reinterpret_cast<const uint16_t *>(tableS + (p.tl.class_feat - p.tl.lutv));
-    tb.stage1 = reinterpret_cast<const latok_stage1_t *>(tableS + (p.tl.stage1 - p.tl.lutv));
-    tb.stage2 = p.table_blob + p.tl.stage2;
-    tb.low_limit = p.tl.low_limit; tb.high_first = p.tl.high_first; tb.high_last = p.tl.high_last; tb.high_feat = p.tl.high_feat;
     const uint32_t *lutv = reinterpret_cast<const uint32_t *>(tableS);
 #ifdef LATOK_PROFILE
     long long _prof_t = clock64();
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         }
         return tma_bytes > 0;
     };
-    auto plain_load = [&](long long r, int b) {          // exact re-analysis: fetch the window again
+    auto plain_load = [&](long long r, int b) {          // repeated analysis: fetch the window again
         uint8_t *X = Xof(b);
         const long long wl = r * (long long)RANGE - LPAD;
         for (int i = lane * 16; i < XBYTES; i += 512) {
@@ -384,51 +389,31 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         if (xin != 0 || Mm) out = eval_backlog(xin, Mm, FmA, S, Lm, HOT);
         return HOT;
     };
-    // exact evaluation: publish this range's transfer function / collect the backlog that enters it from the tile's
-    // backlog-in and the functions of the ranges before it (all warps compute theirs at the same time)
-    auto publish_fn = [&](Fn f, unsigned round) {
-        if (lane == 0) {
-            st_vs32(&ctl.xfu[cw], f.u); st_vs32(&ctl.xfv[cw], f.v);
-            __threadfence_block();
-            st_vs32(reinterpret_cast<int *>(&ctl.xfgen[cw]), (int)round);
-        }
-    };
-    auto backlog_in = [&](int slot, unsigned round) -> int {
-        int fu = 0, fv = NEG, x_tile = 0;
-        if (lane == 0) {                 // the backlog that enters the tile (handed down once the look-back has it)
-            unsigned spins = 0;
-            while ((unsigned)ld_vs32(&ctl.xr[slot]) != round) { if (++spins > (1u << 27)) { atomicOr(&p.result->error, 1u); break; } }
-            x_tile = ld_vs32(&ctl.slot[slot].x_in);
-        }
-        x_tile = __shfl_sync(FULL, x_tile, 0);
-        if (lane < cw) {
-            unsigned spins = 0;
-            while ((unsigned)ld_vs32(reinterpret_cast<const int *>(&ctl.xfgen[lane])) != round) { if (++spins > (1u << 26)) { atomicOr(&p.result->error, 1u); break; } }
-            fu = ld_vs32(&ctl.xfu[lane]); fv = ld_vs32(&ctl.xfv[lane]);
-        }
-        __syncwarp();
-        int x = x_tile;
-        for (int i = 0; i < cw; ++i) x = fn_apply(Fn{__shfl_sync(FULL, fu, i), __shfl_sync(FULL, fv, i)}, x);
-        return x;
-    };
-
     // results of the analysis that are posted right away (the rest goes to ctl.rinfo for pass D)
-    int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0; bool a_irregular = false;
+    int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0, a_u = 0, a_mb1 = 0, a_flags = 0;
 
     // ================================================================================================= analysis
-    auto analyze = [&](const long long r, const int buf, const bool exact, const unsigned round, const int x_init) {
+    // x_init: block-mask backlog entering the range; far_init: the chunk open at the end of the range (a range that does
+    // not end at a chunk closer) will be closed hot.  Both are 0 in the first analysis of every range; the service warp
+    // orders a repeat with the real values where they differ (resolve()).
+    auto analyze = [&](const long long r, const int buf, const int x_init, const int far_init) {
         const long long w0 = r * (long long)RANGE;
         const bool have = r < p.nranges, last_range = r == p.nranges - 1;
-#ifdef LATOK_PROFX
-        long long _px = clock64();
-        if (exact && lane == 0) atomicAdd(&p.result->prof[7], 1ull);
-#endif
         uint8_t *X = Xof(buf);
         uint32_t *tempS = tempof(buf);
-        int c_lo = 0, c_hi = CINF, n_own = 0, ntok_range = 0, lft = -1, v_out = 0, far = 0;
-        bool closed = true, lo_found = true, irregular = false;
+        int c_lo = 0, c_hi = CINF, n_own = 0, ntok_range = 0, lft = -1, v_out = 0;
+        bool closed = true, lo_found = true;
+        // backlog transfer summary of the owned characters: marks - closers, a string boundary (= reset), marks in front of
+        // the first closer, whether there is a closer at all
+        int d_mc = 0, mb1 = 0; uint32_t rs_any = 0; bool seen_cl = false;
         auto finish = [&]() {
-            a_n_own = n_own; a_ntok = ntok_range; a_lft = lft >= 0 ? lft - c_lo : -1; a_v = v_out; a_irregular = irregular;
+            a_n_own = n_own; a_ntok = ntok_range; a_lft = lft >= 0 ? lft - c_lo : -1; a_v = v_out;
+            a_flags = (have ? 1 : 0) | (closed ? 2 : 0) | (lo_found ? 4 : 0) | (seen_cl ? 8 : 0);
+            a_u = 0; a_mb1 = 0;
+            if (have && !lo_found) {               // (the summary exists)
+                a_u = __any_sync(FULL, rs_any != 0u) ? NEG : __reduce_add_sync(FULL, d_mc);
+                a_mb1 = min(__reduce_add_sync(FULL, mb1), 1 << 20);
+            }
             if (lane == 0) {
                 RInfo &ri = ctl.rinfo[cw][buf];
                 ri.c_lo = c_lo; ri.c_hi = c_hi; ri.n_own = n_own; ri.ntok = ntok_range;
@@ -437,11 +422,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             __syncwarp();
         };
         if (!have) {
-            if (exact) {      // pass the backlog on
-                publish_fn(fn_id(), round);
-                v_out = backlog_in(buf, round);
-            }
             c_hi = 0;
+            v_out = x_init;
             finish();
             return;
         }
@@ -459,16 +441,25 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             }
             __syncwarp();
         }
-        // ---- the character in front of the window (prev-context of the first character)
-        // (only matters when the range owns its very first character, i.e. no closer was found in the head window: such a
-        // range is irregular and comes back here with exact = true)
+        // ---- the character in front of the window: prev-context of the window's first character.  Matters only when the
+        // range owns that character, i.e. no closer is found in the head window (then the range begins inside a chunk), and
+        // for the feature rows of the head zone in token-feature mode.  A blank or a newline in the first 100 bytes is a
+        // closer for sure, so almost every range skips this.
         uint32_t prevLB = 0;
-        if ((exact || kFeats) && w0 > 0) {       // (token-feature mode: the feature rows of the head-zone characters are summed too)
-            const uint8_t *q = X + LPAD - 1;
-            int back = 0;
-            while (back < 3 && (q[-back] & 0xC0u) == 0x80u) ++back;
-            const uint32_t w = classify_at(q - back, tb);
-            prevLB = (w & 1u) | (((w >> 1) & 1u) << 1) | (((w >> 3) & 1u) << 2) | (((w >> 5) & 1u) << 3) | (((w >> 6) & 1u) << 4);
+        if (w0 > 0) {
+            bool skip = false;
+            if (!kFeats) {
+                const uint32_t w4 = lane < 25 ? *reinterpret_cast<const uint32_t *>(X + LPAD + 4 * lane) : 0u;
+                const uint32_t t1 = w4 ^ 0x20202020u, t2 = w4 ^ 0x0A0A0A0Au;
+                skip = __any_sync(FULL, ((((t1 - 0x01010101u) & ~t1) | ((t2 - 0x01010101u) & ~t2)) & 0x80808080u) != 0u);
+            }
+            if (!skip) {
+                const uint8_t *q = X + LPAD - 1;
+                int back = 0;
+                while (back < 3 && (q[-back] & 0xC0u) == 0x80u) ++back;
+                const uint32_t w = classify_at(q - back, tb);
+                prevLB = (w & 1u) | (((w >> 1) & 1u) << 1) | (((w >> 3) & 1u) << 2) | (((w >> 5) & 1u) << 3) | (((w >> 6) & 1u) << 4);
+            }
         }
         const bool term_in_win = p.n_bytes < w0 + WIN;
         const long long rem64 = p.n_bytes - w0;
@@ -658,11 +649,23 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     c_hi = cv;
                 }
                 // ---- forward half of the block mask, common case: a carry-propagating add per lane-word
-                uint32_t HOTorM = Mraw;
-                if (!exact) {
+                uint32_t HOTorM;
+                {
                     // characters the block mask runs over: the owned ones (c_hi is still "infinite" before the last step)
                     const uint32_t ACTf = range_mask(c0, c_lo, c_hi) & TRUST;
                     const uint32_t Mm = Mraw & ACTf, CL = CLr & ACTf;
+                    // (summary for resolve(): the range as a backlog transfer function, marks in front of its first closer)
+                    // -- kept only for ranges that begin inside a chunk (the others are asked again if a backlog enters them)
+                    if (!lo_found) {
+                        d_mc += __popc(Mm) - __popc(CL);
+                        rs_any |= (Fm | Lm_raw) & ACTf;
+                    }
+                    if (!lo_found && !seen_cl) {
+                        const unsigned Gc = __ballot_sync(FULL, CL != 0u);
+                        const int fl = Gc ? __ffs(Gc) - 1 : 32;
+                        mb1 += __popc(lane < fl ? Mm : (lane == fl ? (Mm & ((CL & (0u - CL)) - 1u)) : 0u));
+                        seen_cl = Gc != 0u;
+                    }
                     uint32_t co;
                     (void)chunk_carry(Mm, CL, 0u, co);
                     const unsigned G = __ballot_sync(FULL, co != 0u), Pg = __ballot_sync(FULL, CL == 0u && co == 0u);
@@ -700,26 +703,18 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             Fp = Fc; leadp = leadc; np = nc; c0p = c0c;
         }
         PROF5(1);
-        PROFX(0);
         if (c_hi == CINF) c_hi = crun;           // (defensive; every range sets it)
         n_own = c_hi - c_lo;
         if (n_own < 0) n_own = 0;
-        if (!exact) {
-            // not covered here: a range that does not begin / end at a chunk closer.  A backlog left by the range's last
-            // chunk (several marks) is handed to the next range by the service warp (settle)
-            irregular = !lo_found || !closed;
-            v_out = xb;
-            if (lane == 0 && xb != 0) atomicAdd(&p.result->prof[14], 1ull);      // (statistics)
-            if (irregular) {                       // the tile is analysed again by the exact evaluation
-                if (lane == 0) {                   // (statistics: why)
-                    if (!lo_found) atomicAdd(&p.result->prof[12], 1ull);
-                    if (!closed) atomicAdd(&p.result->prof[13], 1ull);
-                }
-                finish(); return;
-            }
+        v_out = xb;
+        if (lane == 0) {                           // (statistics)
+            if (xb != 0) atomicAdd(&p.result->prof[14], 1ull);
+            if (!lo_found) atomicAdd(&p.result->prof[12], 1ull);
+            if (!closed) atomicAdd(&p.result->prof[13], 1ull);
         }
         __syncwarp();
         auto T_at = [&](int js, int w) -> uint32_t & { return tempS[(js * 32 + lane) * TWD + w]; };
+        (void)T_at;
         // character ends its string: the next character (possibly in the next lane-word) starts one
         auto L_of = [&](uint32_t Fm, uint32_t pk) -> uint32_t {
             const int n = pk_n(pk);
@@ -729,79 +724,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             const bool has_term = (unsigned)(nb_win - (js * STEP + lane * 32)) < 32u;
             return mask_lt(n - (has_term ? 1 : 0));
         };
-        auto act_mask = [&](int js, int n, int c0) -> uint32_t {
-            const uint32_t REAL = real_mask(js, n);
-            if (closed) return range_mask(c0, c_lo, c_hi) & REAL;
-            uint32_t TRUST = REAL;
-            if (js == RS - 1 && lane == 31 && !term_in_win) TRUST &= mask_lt(__popc(sbmS[js * 32 + lane] & mask_lt(32 - MARGIN)));
-            return range_mask(c0, c_lo, CINF) & TRUST;
-        };
-        // ---------------------------------------------------------------- pass B (exact only): backlog mark by mark
-        if (exact) {
-            // B1: the range as one transfer function (up to the last owned character), for the ranges after this one
-            {
-                Fn rf = fn_id();
-#pragma unroll 1
-                for (int js = 0; js < RS; ++js) {
-                    const uint32_t pk = T_at(js, I_K);
-                    const int n = pk_n(pk), c0 = pk_c0(pk);
-                    const uint32_t ACT = act_mask(js, n, c0);
-                    const uint32_t Fr = T_at(js, I_F);
-                    const Fn inc = lane_fn_scan(T_at(js, I_H) & ACT, Fr & ACT, T_at(js, I_S) & ACT, L_of(Fr, pk) & ACT);
-                    const int src = (js == RS - 1 && !closed) ? 32 - HLANES - 1 : 31;
-                    rf = fn_compose(rf, Fn{__shfl_sync(FULL, inc.u, src), __shfl_sync(FULL, inc.v, src)});
-                }
-                publish_fn(rf, round);
-            }
-            PROFX(1);
-            // B2: the backlog that really enters, then mark by mark
-            int x = backlog_in(buf, round);
-            PROFX(2);
-            int v_nom = 0;
-#pragma unroll 1
-            for (int js = 0; js < RS; ++js) {
-                const uint32_t pk = T_at(js, I_K);
-                const int n = pk_n(pk), c0 = pk_c0(pk);
-                const uint32_t ACT = act_mask(js, n, c0);
-                const uint32_t Fr = T_at(js, I_F);
-                const uint32_t S = T_at(js, I_S) & ACT, Lm = L_of(Fr, pk) & ACT, Mm = T_at(js, I_H) & ACT, FmA = Fr & ACT;
-                int out;
-                const uint32_t HOT = exact_step(x, Mm, FmA, S, Lm, out);
-                x = __shfl_sync(FULL, out, 31);
-                if (js == RS - 1) v_nom = __shfl_sync(FULL, out, 32 - HLANES - 1);
-                T_at(js, I_H) = HOT;
-            }
-            v_out = closed ? x : v_nom;
-            PROFX(3);
-            // the chunk still open at the end of the trusted halo: hot if a backlog is pending, else look ahead for a mark
-            if (!closed) {
-                const uint32_t pk = T_at(RS - 1, I_K);
-                const int n = pk_n(pk), c0 = pk_c0(pk);
-                const uint32_t ACT = act_mask(RS - 1, n, c0);
-                const uint32_t CL = (T_at(RS - 1, I_S) | L_of(T_at(RS - 1, I_F), pk)) & ACT;
-                const unsigned H = __ballot_sync(FULL, CL != 0u);
-                const unsigned above = H & (0xFFFFFFFFu << (32 - HLANES));
-                bool nw = false;
-                if (lane == 32 - HLANES - 1) {
-                    const int nr = __popc(ACT);
-                    nw = nr > 0 && ((CL >> (nr - 1)) & 1u) == 0u && above == 0u;
-                }
-                const bool need_walk = __shfl_sync(FULL, nw ? 1 : 0, 32 - HLANES - 1) != 0;
-                if (need_walk) {
-                    if (x >= 1) far = 1;
-                    else {
-                        const bool any = walk_ahead(p, tb, w0 + WIN - MARGIN, lane);
-                        far = any ? 1 : 0;
-                        if (lane == 0) atomicAdd(&p.result->walks, 1ull);
-                    }
-                }
-            }
-        }
         PROF5(2);
-        PROFX(4);
         // ---------------------------------------------------------------- pass C: blanked chunks, values, tokens
         {
-            uint32_t bin_step = (uint32_t)far;
+            uint32_t bin_step = (uint32_t)far_init;
             int nsa_carry = -1;
             int lft_max = -1;
 #pragma unroll 1
@@ -821,8 +747,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 const int n = pk_n(pk), c0 = pk_c0(pk);
                 const uint32_t REAL = real_mask(js, n);
                 const uint32_t OWN = range_mask(c0, c_lo, c_hi) & REAL;
-                const uint32_t ACT = closed ? OWN : act_mask(js, n, c0);
-                const uint32_t CL = (Sraw | L_of(Fm, pk)) & ACT;
+                const uint32_t CL = (Sraw | L_of(Fm, pk)) & OWN;
                 HOT &= CL;
                 const bool hasCL = CL != 0u;
                 const bool firstHot = hasCL && (HOT & (CL & (0u - CL))) != 0u;
@@ -888,11 +813,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         }
         finish();
         PROF5(3);
-        PROFX(5);
     };
 
     // ================================================================================================= output
-    auto output = [&](const long long r, const int buf, unsigned long long G_in, unsigned long long K_in, unsigned long long base_in, bool direct_spans) {
+    auto output = [&](const long long r, const int buf, unsigned long long G_in, unsigned long long K_in, unsigned long long base_in) {
         const RInfo ri = ctl.rinfo[cw][buf];
         const bool have = (ri.flags & 1) != 0, closed = (ri.flags & 2) != 0, lo_found = (ri.flags & 4) != 0, last_range = (ri.flags & 8) != 0;
         if (!have) return;
@@ -915,7 +839,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         int ktok = 0;                      // tokens of the range before this step
         unsigned fc[7] = {0, 0, 0, 0, 0, 0, 0};      // token-feature mode: sums of the token open at the end of the previous step
         bool fc_hit = false;                          // ... and whether its first character has been seen
-        const bool spans_direct_all = direct_spans || !closed || !lo_found ||
+        const bool spans_direct_all = !closed || !lo_found ||
                                       K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens;   // (the direct path checks every pair)
 #pragma unroll 1
         for (int js = 0; js < RS; ++js) {
@@ -1294,7 +1218,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     auto post = [&](int s) {
         if (lane == 0) {
             WAgg &a = ctl.wagg[s][cw];
-            a.n_own = a_n_own; a.ntok = a_ntok; a.lft = a_lft; a.v = a_v; a.flags = a_irregular ? 1 : 0;
+            a.n_own = a_n_own; a.ntok = a_ntok; a.lft = a_lft; a.v = a_v; a.flags = a_flags; a.u = a_u; a.mb1 = a_mb1;
             __threadfence_block();
         }
         __syncwarp();
@@ -1307,33 +1231,21 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         }
         phase_bits ^= 1u << b;
     };
-    // write out tile `tile` (iteration kk): wait for its prefix (running the exact evaluation if asked to), then pass D
-    unsigned round = 0;
+    // write out tile `tile` (iteration kk): wait for its prefix (repeating the analysis if asked to), then pass D
     auto finish_tile = [&](int tile, int kk) {
         const int s = kk & 1;
         const long long r = (long long)tile * NW + cw;
-        bool exact_done = false;
         for (;;) {
             nb_sync(BAR_PRE + s, NTH);
             const int mode = ctl.slot[s].mode;
             if (mode == 0) break;
-            // mode 1: the exact evaluation of the whole tile.  mode 2: a backlog enters this range after all -- its ordinary
-            // analysis once more, with it (the other ranges of the tile just answer; what they posted stands).
-            // (ONE call site for both: a second inlined copy of the analysis costs the regular path instruction-cache misses)
-            int px = 0;
-            if (mode == 2) {
-                px = ld_vs32(&ctl.patch_x[cw]);
-                if (px < 0 || r >= p.nranges) { nb_arrive(BAR_AGG + s, NTH); continue; }
-            } else ++round;
-#ifdef LATOK_PROFX
-            const long long _pl = clock64();
-#endif
-            if (r < p.nranges) plain_load(r, s);
-#ifdef LATOK_PROFX
-            if (lane == 0) atomicAdd(&p.result->prof[6], (unsigned long long)(clock64() - _pl));
-#endif
-            analyze(r, s, mode == 1, round, px);
-            if (mode == 1) exact_done = true;
+            // mode 2: a backlog enters this range after all, or the chunk open at its end will be closed hot -- its ordinary
+            // analysis once more, with them (the other ranges of the tile just answer; what they posted stands).
+            // (ONE more call site only: every inlined copy of the analysis costs the regular path instruction-cache misses)
+            const int px = ld_vs32(&ctl.patch_x[cw]), pfar = ld_vs32(&ctl.patch_far[cw]);
+            if (px < 0 || r >= p.nranges) { nb_arrive(BAR_AGG + s, NTH); continue; }
+            plain_load(r, s);
+            analyze(r, s, px, pfar);
             post(s);
         }
         PROF5(4);
@@ -1356,7 +1268,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             G_in = sl.G + (unsigned long long)pn; K_in = sl.K + (unsigned long long)pkk;
             base_in = hl ? sl.G + (unsigned long long)lv : sl.base;
         }
-        output(r, s, G_in, K_in, base_in, exact_done);
+        output(r, s, G_in, K_in, base_in);
         PROF5(5);
     };
 
@@ -1370,7 +1282,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             if (s == 0 ? pending[0] : pending[1]) wait_window(s, phase_bits);
             __syncwarp();
             PROF5(0);
-            analyze((long long)tile_cur * NW + cw, s, false, 0u, 0);
+            analyze((long long)tile_cur * NW + cw, s, 0, 0);
             post(s);
         } else {
             nb_arrive(BAR_AGG + s, NTH);                 // tells the service warp that the tickets have run out
