@@ -44,6 +44,7 @@ constexpr int WIN = RS * STEP;
 constexpr int HALO = V5_HALO;
 constexpr int HLANES = HALO / 32;
 constexpr int RANGE = V5_RANGE;
+constexpr int NMB = 7;                   // feature planes a non-ASCII character can have (ALPHA .. SYMBOL)
 constexpr int MARGIN = 12;               // characters starting in the last 12 window bytes lack forward context
 constexpr int LPAD = 16;                 // bytes in front of the window (previous character)
 constexpr int XBYTES = LPAD + WIN + 16;
@@ -102,6 +103,13 @@ __host__ __device__ inline Plan plan(const TableLayout &tl, bool is_default)
 #define PROF5(i) do { } while (0)
 #endif
 
+#ifndef LATOK_NO_HINTS
+#define LIKELY(x) (__builtin_expect(!!(x), 1))
+#define UNLIKELY(x) (__builtin_expect(!!(x), 0))
+#else
+#define LIKELY(x) (x)
+#define UNLIKELY(x) (x)
+#endif
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int CINF = 0x3FFFFFFF;
 
@@ -112,6 +120,7 @@ __device__ __forceinline__ int pk_c0(uint32_t k) { return (int)((k >> 6) & 8191u
 __device__ __forceinline__ int pk_tp(uint32_t k) { return (int)((k >> 19) & 2047u); }
 __device__ __forceinline__ uint32_t pk_ps(uint32_t k) { return (k >> 30) & 1u; }
 
+__device__ __forceinline__ int bfind32(uint32_t x) { int r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x)); return r; }   // index of the highest set bit (-1: none)
 __device__ __forceinline__ int ld_vs32(const int *p) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p))); return v; }
 __device__ __forceinline__ void st_vs32(int *p, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory"); }
 
@@ -503,12 +512,18 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     return __funnelshift_r(w[0], w[1], 8 * (k & 3));
                 };
                 Fc = sb;
-                if (!__any_sync(FULL, (mm & (mm - 1u)) != 0u)) {
+                if (LIKELY(!__any_sync(FULL, (mm & (mm - 1u)) != 0u))) {
                     if (mm) {
                         const int k = __ffs(mm) - 1;
                         const uint32_t fw = mb_features(four_bytes(k), tb), bitk = 1u << k;
+                        // (a character outside ASCII has none of TWITTER @ : / . -- planes 7..11 -- unless it is an over-long
+                        // form of an ASCII character)
 #pragma unroll
-                        for (int f = 0; f < NBASE; ++f) if (fw & (1u << f)) Pc[f] |= bitk;
+                        for (int f = 0; f < NMB; ++f) if (fw & (1u << f)) Pc[f] |= bitk;
+                        if (UNLIKELY(fw >> NMB)) {
+#pragma unroll
+                            for (int f = NMB; f < NBASE; ++f) if (fw & (1u << f)) Pc[f] |= bitk;
+                        }
                     }
                     squeeze_planes<NBASE>(Pc, Fc, leadc, valid);
                 } else {
@@ -520,9 +535,16 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                         const uint32_t fw0 = mb_features(v0, tb), fw1 = two ? mb_features(v1, tb) : 0u;
                         const uint32_t bit0 = 1u << k0, bit1 = 1u << k1;
 #pragma unroll
-                        for (int f = 0; f < NBASE; ++f) {
+                        for (int f = 0; f < NMB; ++f) {
                             if (fw0 & (1u << f)) Pc[f] |= bit0;
                             if (fw1 & (1u << f)) Pc[f] |= bit1;
+                        }
+                        if (UNLIKELY((fw0 | fw1) >> NMB)) {
+#pragma unroll
+                            for (int f = NMB; f < NBASE; ++f) {
+                                if (fw0 & (1u << f)) Pc[f] |= bit0;
+                                if (fw1 & (1u << f)) Pc[f] |= bit1;
+                            }
                         }
                     }
                     const uint32_t del = leadc ? (~leadc & valid) : 0u;
@@ -535,7 +557,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += t; }
                 c0c = crun + sc - nc;
                 crun += __shfl_sync(FULL, sc, 31);
-                if (j == jt) c_hi = __shfl_sync(FULL, c0c + __popc(leadc & mask_lt(bt)), lt);
+                if (UNLIKELY(j == jt)) c_hi = __shfl_sync(FULL, c0c + __popc(leadc & mask_lt(bt)), lt);
             }
             // -------------------------------------------------------------- context + rules of step j-1
             if (j > 0) {
@@ -656,11 +678,11 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     const uint32_t Mm = Mraw & ACTf, CL = CLr & ACTf;
                     // (summary for resolve(): the range as a backlog transfer function, marks in front of its first closer)
                     // -- kept only for ranges that begin inside a chunk (the others are asked again if a backlog enters them)
-                    if (!lo_found) {
+                    if (UNLIKELY(!lo_found)) {
                         d_mc += __popc(Mm) - __popc(CL);
                         rs_any |= (Fm | Lm_raw) & ACTf;
                     }
-                    if (!lo_found && !seen_cl) {
+                    if (UNLIKELY(!lo_found && !seen_cl)) {
                         const unsigned Gc = __ballot_sync(FULL, CL != 0u);
                         const int fl = Gc ? __ffs(Gc) - 1 : 32;
                         mb1 += __popc(lane < fl ? Mm : (lane == fl ? (Mm & ((CL & (0u - CL)) - 1u)) : 0u));
@@ -672,7 +694,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     const unsigned long long sum = (unsigned long long)(G | Pg) + (unsigned long long)G + (unsigned long long)(xb != 0 ? 1u : 0u);
                     const uint32_t cin = (((uint32_t)sum ^ Pg) >> lane) & 1u;
                     const uint32_t T = chunk_carry(Mm, CL, cin, co);
-                    if (xb < 2 && !__any_sync(FULL, (Mm & ~CL & T) != 0u)) {
+                    if (LIKELY(xb < 2 && !__any_sync(FULL, (Mm & ~CL & T) != 0u))) {
                         HOTorM = T & CL;
                         xb = (int)((sum >> 32) & 1u);
                     } else {
@@ -925,7 +947,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 uint8_t *bst = reinterpret_cast<uint8_t *>(tst);                    // (the token stage is idle here)
                 *reinterpret_cast<uint4 *>(bst + p0) = c1;
                 *reinterpret_cast<uint4 *>(bst + p0 + 16) = c2;
-                if (be > 1024) {          // stream positions 1024.. (the step holds up to 1025 characters, plus the alignment)
+                if (UNLIKELY(be > 1024)) {          // stream positions 1024.. (the step holds up to 1025 characters, plus the alignment)
                     uint32_t Vt[NV];
 #pragma unroll
                     for (int q = 0; q < NV; ++q) Vt[q] = bp[q * 36 + 32];
@@ -977,7 +999,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     nextsplit = above ? got : ctl.nsa[cw][buf][js];
                 }
                 const bool multi_f = __any_sync(FULL, (FO & (FO - 1u)) != 0u);      // two string starts inside one lane-word
-                if (!direct && !multi_f) {
+                if (LIKELY(!direct && !multi_f)) {
                     // bit-reversed planes: __clz walks the tokens in ascending order, the first split after a token is the
                     // highest bit below it.  At most one string start per lane-word here.
                     // (positions are handled as q = 31 - position, the index FLO returns on the reversed planes)
@@ -985,17 +1007,23 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     const uint32_t spr = __brev(SPq), e2r = __brev(E & ~SPLIT);     // e2r: the span began one character earlier
                     const int fq = FO ? (int)__clz(FO) : -64;                        // q of the string start inside this lane-word
                     const int offA = c0 - lf_excl + 31, offB = fq;                   // string-relative index = off - q
-                    const int nse = nextsplit >= 0 ? 31 - (nextsplit - c0) : (1 << 28);
                     int2 *dp = tst + ka + tp;
+                    // the lowest token bit is the only one that may have no split below it inside the lane-word: the loop
+                    // does not test for that, the pair is put right afterwards
+                    const uint32_t lowb = evr & (0u - evr);
+                    const bool fix_last = evr != 0u && (spr & (lowb - 1u)) == 0u;
                     while (evr) {
-                        const int q = 31 - __clz(evr);                              // FLO
-                        const uint32_t bit = 1u << q;
-                        evr ^= bit;
+                        const int q = bfind32(evr);                                  // FLO
+                        const uint32_t below = (1u << q) - 1u;
+                        evr &= below;
                         const int off = q <= fq ? offB : offA;
-                        const uint32_t ab = spr & (bit - 1u);
-                        const int qe = ab ? 31 - __clz(ab) : nse;                    // FLO; the first split after the token
-                        const int sidx = off - q - ((e2r & bit) ? 1 : 0);
-                        *dp++ = make_int2(sidx, off - qe);
+                        const int qe = bfind32(spr & below);                         // FLO; the first split after the token
+                        *dp++ = make_int2(off - q - (int)((e2r >> q) & 1u), off - qe);
+                    }
+                    if (fix_last) {
+                        const int ql = bfind32(lowb);
+                        const int off = ql <= fq ? offB : offA;
+                        dp[-1].y = nextsplit >= 0 ? off - 31 + (nextsplit - c0) : -1;
                     }
                 } else {
                 uint32_t ev = E;
@@ -1022,7 +1050,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 }
                 // a range whose head is not chunk-aligned: its first split that follows a non-space character ends the
                 // token left open by earlier ranges
-                if (!lo_found && r > 0) {
+                if (UNLIKELY(!lo_found && r > 0)) {
                     const uint32_t PSr = (Sraw << 1) | pk_ps(pk);
                     // (a range that ends at a closer also answers for the character after it: the next range begins at a
                     // closer then and does not come here -- a token that covers this whole range may end exactly there)

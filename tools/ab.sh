@@ -6,6 +6,6 @@ IFS=';' read -ra WLS <<< "${AB_WL:-tweets 1000000 4 3;mixed 1000000 4 3;mixed 10
 for lib in "$@" ""; do
   for wl in "${WLS[@]}"; do
     echo "== ${lib:-in-tree} $wl"
-    LATOK_B200_LIB=$lib python tools/prof_run.py $wl 2>&1 | tail -2
+    LATOK_B200_LIB=$lib python tools/prof_run.py $wl 2>&1 | tail -1
   done
 done
