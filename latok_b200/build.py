@@ -68,25 +68,52 @@ def _stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+# latok_tok5.cu is compiled a second time for the short-string geometry (see the head of that file)
+SHORT_DEFS = ["-DLATOK_V5_SHORT", "-DLATOK_V5_RS=3", "-DLATOK_V5_NW=11"]
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale():
         return LIB
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
     subprocess.run([sys.executable, str(ROOT / "tools" / "gen_tables.py")], check=True,
                    stdout=None if verbose else subprocess.DEVNULL)
-    cmd = [find_nvcc(), *NVCC_FLAGS]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    extra = []
     if os.environ.get("LATOK_PROFILE"):
-        cmd += ["-DLATOK_PROFILE"]
+        extra += ["-DLATOK_PROFILE"]
     if os.environ.get("LATOK_DEFS"):
-        cmd += os.environ["LATOK_DEFS"].split()
+        extra += os.environ["LATOK_DEFS"].split()
     if verbose:
-        cmd += ["-Xptxas", "-v"]
+        extra += ["-Xptxas", "-v"]
     # LATOK_B200_LIB_OUT: build somewhere else (e.g. a library for a newer UCD: LATOK_CLASSES / LATOK_LOW_LIMIT are read
     # by tools/gen_tables.py; the next default build regenerates the UCD-11 tables)
     out = Path(os.environ.get("LATOK_B200_LIB_OUT") or LIB)
-    cmd += [str(s) for s in SOURCES] + ["-lz", "-o", str(out)]        # zlib: the csv.gz reader (latok_reader.cpp)
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+    nvcc = find_nvcc()
+    with tempfile.TemporaryDirectory() as tmp:
+        jobs = [(src, [], Path(tmp) / (src.stem + ".o")) for src in SOURCES]
+        jobs.append((CSRC / "latok_tok5.cu", SHORT_DEFS, Path(tmp) / "latok_tok5_short.o"))
+
+        def compile_one(job):
+            src, defs, obj = job
+            cmd = [nvcc, *flags, *extra, *defs, "-c", str(src), "-o", str(obj)]
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            return r.returncode, r.stdout + r.stderr
+
+        with ThreadPoolExecutor(len(jobs)) as pool:
+            results = list(pool.map(compile_one, jobs))
+        for rc, log in results:
+            if verbose or rc:
+                sys.stderr.write(log)
+        if any(rc for rc, _ in results):
+            raise subprocess.CalledProcessError(1, "nvcc -c")
+        cmd = [nvcc, *NVCC_FLAGS, *[str(o) for _, _, o in jobs], "-lz", "-o", str(out)]      # zlib: the csv.gz reader
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
     return out
 
 

@@ -373,19 +373,26 @@ __global__ void narrow_spans_kernel(const int2 *spans, uint32_t *out, Result *re
 static int run_device(latok_b200_engine *e, Batch &b)
 {
     // the matrix mode runs the v4 kernel (one CTA per 7 936-byte tile); everything else (split mask, spans, token
-    // features) runs v5 (one warp per 3 968-byte range, V5_NW ranges per tile)
+    // features) runs v5 (one warp per range, a tile = the ranges of one CTA) in one of its two geometries: short strings
+    // (3 KB ranges, 11 compute warps per CTA) or long strings (4 KB ranges, 9 warps: fewer range boundaries inside
+    // space-free runs), by the average string length of the batch (LATOK_B200_GEOMETRY=short|long overrides)
     const bool words = (b.what & LATOK_B200_MATRIX) != 0, feats = (b.what & LATOK_B200_FEATS) != 0;
     const bool use5 = !words && !getenv("LATOK_B200_FORCE_V4");
-    const int unit = use5 ? V5_RANGE : TILE;
+    bool shortg = b.n_bytes < 4096LL * (b.n_strings > 0 ? b.n_strings : 1);
+    if (const char *g = getenv("LATOK_B200_GEOMETRY")) shortg = g[0] == 's';
+    const int range5 = shortg ? tokenize5_range_bytes_short() : tokenize5_range_bytes();
+    const int nw5 = shortg ? tokenize5_ranges_per_tile_short() : tokenize5_ranges_per_tile();
+    const int unit = use5 ? range5 : TILE;
     const long long nunits = b.n_bytes / unit + 1;
-    const long long ntiles = use5 ? (nunits + V5_NW - 1) / V5_NW : nunits;
+    const long long ntiles = use5 ? (nunits + nw5 - 1) / nw5 : nunits;
+    const size_t plane_words = shortg ? tokenize5_plane_words_short(nunits) : tokenize5_plane_words(nunits);
     if (int r = b.d_first.ensure((size_t)nunits + 1)) return r;
     // the status word of every aggregate record carries the launch epoch, so records are zeroed only when (re)allocated
     // (agg / inc / osum / planes are shared by the two sets: tokenize kernels run one after the other on one stream)
     if ((size_t)ntiles > e->agg.cap) { CU(cudaStreamSynchronize(e->stream)); if (int r = e->agg.ensure((size_t)ntiles, true)) return r; }
     if ((size_t)ntiles > e->inc.cap) { CU(cudaStreamSynchronize(e->stream)); if (int r = e->inc.ensure((size_t)ntiles)) return r; }
     if (feats && (size_t)(use5 ? nunits : ntiles) > e->osum.cap) { CU(cudaStreamSynchronize(e->stream)); if (int r = e->osum.ensure((size_t)(use5 ? nunits : ntiles), true)) return r; }
-    if (feats && use5 && tokenize5_plane_words(nunits) > e->d_planes.cap) { CU(cudaStreamSynchronize(e->stream)); if (int r = e->d_planes.ensure(tokenize5_plane_words(nunits))) return r; }
+    if (feats && use5 && plane_words > e->d_planes.cap) { CU(cudaStreamSynchronize(e->stream)); if (int r = e->d_planes.ensure(plane_words)) return r; }
     if (int r = b.d_splits.ensure((size_t)b.n_bytes + 64)) return r;
     if (int r = b.d_char_off.ensure((size_t)b.n_strings + 1)) return r;
     if (int r = b.d_tok_off.ensure((size_t)b.n_strings + 1)) return r;
@@ -411,8 +418,9 @@ static int run_device(latok_b200_engine *e, Batch &b)
     p.ticket = &b.d_result.p->ticket; p.ticket_base = 0;
     p.result = b.d_result.p;
     p.table_blob = e->d_table.p; p.tl = e->tl; p.rules = e->rules;
-    int grid = e->n_sm * (use5 ? tokenize5_ctas_per_sm(e->tl, e->rules.is_default != 0, feats)
-                               : tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words, feats));
+    int grid = e->n_sm * (!use5 ? tokenize_ctas_per_sm(e->tl, e->rules.is_default != 0, words, feats)
+                          : shortg ? tokenize5_ctas_per_sm_short(e->tl, e->rules.is_default != 0, feats)
+                                   : tokenize5_ctas_per_sm(e->tl, e->rules.is_default != 0, feats));
     if ((long long)grid > ntiles) grid = (int)ntiles;
     if (!use5) { if (int r = e->span_scratch.ensure((size_t)grid * 2 * SPAN_SCRATCH)) return r; }
     p.span_scratch = e->span_scratch.p;
@@ -427,7 +435,7 @@ static int run_device(latok_b200_engine *e, Batch &b)
     if (b.inputs_on_stream) CU(cudaStreamWaitEvent(e->stream, b.ev_h2d, 0));
     CU(cudaStreamWaitEvent(e->stream, b.ev_index, 0));
     CU(cudaEventRecord(b.ev_k0, e->stream));
-    CU(use5 ? launch_tokenize5(p, grid, e->stream) : launch_tokenize(p, grid, e->stream));
+    CU(!use5 ? launch_tokenize(p, grid, e->stream) : shortg ? launch_tokenize5_short(p, grid, e->stream) : launch_tokenize5(p, grid, e->stream));
     CU(cudaEventRecord(b.ev_k1, e->stream));
     e->launches += 2;
     if (b.what & LATOK_B200_SPANS16) {

@@ -454,9 +454,13 @@ __device__ __forceinline__ uint32_t mb_features(uint32_t v, const Tables &t)
     const uint32_t blk = t.stage1[cl >> 7];
     const uint32_t b = t.stage2[blk * 64u + ((cl & 127u) >> 1)];
     uint32_t fw = t.class_feat[(b >> ((cl & 1u) * 4u)) & 15u];
-    if (cp >= t.low_limit) fw = (cp >= t.high_first && cp <= t.high_last) ? t.high_feat : 0u;
-    if (cp < 0x80u) fw = t.ascii_feat[cp];                     // over-long form of an ASCII character
-    if (L > 3) fw = 0u;                                        // 0xF8..0xFF: no features
+    // the three rare cases behind one test: beyond the two-stage table, an over-long form of an ASCII character
+    // (cp - 0x80 wraps), an invalid lead byte 0xF8..0xFF
+    if (__builtin_expect(cp - 0x80u >= t.low_limit - 0x80u || L > 3, 0)) {
+        if (cp >= t.low_limit) fw = (cp >= t.high_first && cp <= t.high_last) ? t.high_feat : 0u;
+        if (cp < 0x80u) fw = t.ascii_feat[cp];
+        if (L > 3) fw = 0u;
+    }
     return fw;
 }
 

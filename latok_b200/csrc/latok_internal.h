@@ -130,9 +130,17 @@ struct Params {
 
 size_t tokenize_smem_bytes(const TableLayout &tl, bool want_words, bool want_feats);
 int tokenize_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_words, bool want_feats);
+// the v5 kernel exists in two geometries (latok_tok5.cu is compiled twice): long strings / short strings (_short)
+int tokenize5_range_bytes();
+int tokenize5_ranges_per_tile();
 int tokenize5_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_feats);
 size_t tokenize5_plane_words(long long nranges);
 cudaError_t launch_tokenize5(const Params &p, int grid, cudaStream_t s);
+int tokenize5_range_bytes_short();
+int tokenize5_ranges_per_tile_short();
+int tokenize5_ctas_per_sm_short(const TableLayout &tl, bool is_default, bool want_feats);
+size_t tokenize5_plane_words_short(long long nranges);
+cudaError_t launch_tokenize5_short(const Params &p, int grid, cudaStream_t s);
 cudaError_t launch_tile_index(const long long *offsets, long long n_strings, long long n_bytes,
                               long long *tile_first_str, long long ntiles, int tile_bytes, Result *result, cudaStream_t s);
 cudaError_t launch_tokenize(const Params &p, int grid, cudaStream_t s);

@@ -33,8 +33,20 @@
 // No tensor cores: nothing here is a dense contraction; the bound is HBM bandwidth.
 #include "latok_device.cuh"
 
+// This file is compiled TWICE into the library (latok_b200/build.py): the geometry for long strings (4 KB ranges, 9
+// compute warps per CTA -- fewer range boundaries inside space-free runs) and, with -DLATOK_V5_SHORT -DLATOK_V5_RS=3
+// -DLATOK_V5_NW=11, the geometry for short strings (3 KB ranges, 11 compute warps per CTA at 80 registers: more warps
+// in flight, which is what the instruction-bound regular path gains from).  The host picks one per batch.
+#ifdef LATOK_V5_SHORT
+#define V5NS v5s
+#define V5FN(name) name##_short
+#else
+#define V5NS v5
+#define V5FN(name) name
+#endif
+
 namespace latok {
-namespace v5 {
+namespace V5NS {
 
 constexpr int NW = V5_NW;                  // compute warps per CTA (the service warp is warp NW)
 constexpr int NTH = (NW + 1) * 32;
@@ -1349,23 +1361,23 @@ static int ctas_one(const TableLayout &tl)
     return nb < 1 ? 1 : nb;
 }
 
-}  // namespace v5
+}  // namespace V5NS
 
-int tokenize5_range_bytes() { return v5::RANGE; }
-int tokenize5_ranges_per_tile() { return v5::NW; }
-size_t tokenize5_plane_words(long long nranges) { return (size_t)nranges * v5::RS * NFEAT * 32; }
+int V5FN(tokenize5_range_bytes)() { return V5NS::RANGE; }
+int V5FN(tokenize5_ranges_per_tile)() { return V5NS::NW; }
+size_t V5FN(tokenize5_plane_words)(long long nranges) { return (size_t)nranges * V5NS::RS * NFEAT * 32; }
 
-int tokenize5_ctas_per_sm(const TableLayout &tl, bool is_default, bool want_feats)
+int V5FN(tokenize5_ctas_per_sm)(const TableLayout &tl, bool is_default, bool want_feats)
 {
-    if (is_default) return want_feats ? v5::ctas_one<true, true>(tl) : v5::ctas_one<true, false>(tl);
-    return want_feats ? v5::ctas_one<false, true>(tl) : v5::ctas_one<false, false>(tl);
+    if (is_default) return want_feats ? V5NS::ctas_one<true, true>(tl) : V5NS::ctas_one<true, false>(tl);
+    return want_feats ? V5NS::ctas_one<false, true>(tl) : V5NS::ctas_one<false, false>(tl);
 }
 
-cudaError_t launch_tokenize5(const Params &p, int grid, cudaStream_t s)
+cudaError_t V5FN(launch_tokenize5)(const Params &p, int grid, cudaStream_t s)
 {
     const bool feats = (p.what & 4u) != 0u;
-    if (p.rules.is_default) return feats ? v5::launch_one<true, true>(p, grid, s) : v5::launch_one<true, false>(p, grid, s);
-    return feats ? v5::launch_one<false, true>(p, grid, s) : v5::launch_one<false, false>(p, grid, s);
+    if (p.rules.is_default) return feats ? V5NS::launch_one<true, true>(p, grid, s) : V5NS::launch_one<true, false>(p, grid, s);
+    return feats ? V5NS::launch_one<false, true>(p, grid, s) : V5NS::launch_one<false, false>(p, grid, s);
 }
 
 }  // namespace latok

@@ -16,15 +16,24 @@ from test_gpu_parity import check_batch
 
 pytestmark = pytest.mark.gpu
 
-RANGE, TILE5, STEP = 3968, 9 * 3968, 1024
+STEP = 1024
+GEOMETRIES = {"long": (3968, 9 * 3968), "short": (2944, 11 * 2944)}       # (range, tile) bytes of the two kernel geometries
 
 
-@pytest.fixture(scope="module")
-def engine():
+@pytest.fixture(scope="module", params=["long", "short"])
+def engine(request):
+    """Every test of this module runs with each geometry of the kernel forced (LATOK_B200_GEOMETRY is read at every
+    submit); the sweeps use that geometry's range and tile sizes."""
     from latok_b200.engine import Engine
+    old = os.environ.pop("LATOK_B200_GEOMETRY", None)
+    os.environ["LATOK_B200_GEOMETRY"] = request.param
     e = Engine(0)
+    e.geometry = GEOMETRIES[request.param]
     yield e
     e.close()
+    os.environ.pop("LATOK_B200_GEOMETRY", None)
+    if old is not None:
+        os.environ["LATOK_B200_GEOMETRY"] = old
 
 
 def _drift(ch, unit_chars, count, spread=12):
@@ -34,6 +43,7 @@ def _drift(ch, unit_chars, count, spread=12):
 
 @pytest.mark.parametrize("ch,width", [("x", 1), ("é", 2), ("日", 3), ("\U00020000", 4), (",", 1), ("A", 1)])
 def test_split_free_strings_around_a_range(engine, ch, width):
+    RANGE, TILE5 = engine.geometry
     # no split point inside (or, for ',' and 'A', a symbol / upper-case run): one token per string, ends drift over the
     # closer search windows of consecutive ranges
     texts = _drift(ch, RANGE // width, 600) + _drift(ch, 2 * RANGE // width, 300) + _drift(ch, STEP // width, 400, 5)
@@ -41,12 +51,14 @@ def test_split_free_strings_around_a_range(engine, ch, width):
 
 
 def test_split_free_strings_around_a_tile(engine):
+    RANGE, TILE5 = engine.geometry
     texts = _drift("x", TILE5, 60, 20) + _drift("日", TILE5 // 3, 60, 20) + _drift("x", 7936, 120, 10)
     check_batch(engine, texts, 15, label="drift tile")
 
 
 @pytest.mark.parametrize("sep", [" ", " a@b,c@d ", "　", " #tag "])
 def test_one_separator_drifting_through_long_strings(engine, sep):
+    RANGE, TILE5 = engine.geometry
     # a single closer / multi-mark chunk inside an otherwise split-free string of about two ranges
     texts = []
     for k in range(500):
@@ -71,6 +83,7 @@ def test_token_bytes_around_words_and_groups(engine):
 
 
 def test_tokens_spanning_whole_ranges_and_tiles(engine):
+    RANGE, TILE5 = engine.geometry
     # one token that covers 2, 3 and 10 whole ranges (the last one crosses a tile boundary), started and ended at
     # drifting offsets; once with spans only and once with token features (the open-token sums chain, `osum`)
     texts = []

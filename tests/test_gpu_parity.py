@@ -12,18 +12,29 @@ from oracle import oracle
 pytestmark = pytest.mark.gpu
 
 ALL = 1 | 2 | 4 | 8
-# bytes owned per unit of work (latok_internal.h): a v5 range (one warp), a v4 tile (token-feature / matrix modes) and a
-# v5 tile (8 ranges, one look-back record); tests place interesting things around multiples of each
-UNITS = (3968, 7936, 9 * 3968)
+# bytes owned per unit of work (latok_internal.h): a v5 range (one warp) and a v5 tile (the ranges of one CTA, one
+# look-back record) in both geometries of the kernel (long strings: 3 968-byte ranges x 9, short strings: 2 944 x 11),
+# and a v4 tile (matrix mode); tests place interesting things around multiples of each
+RANGES = (3968, 2944)
+UNITS = (3968, 7936, 9 * 3968, 2944, 11 * 2944)
 TILE = 7936
 
 
-@pytest.fixture(scope="module")
-def engine():
+@pytest.fixture(scope="module", params=["auto", "long", "short"])
+def engine(request):
+    """Every test of this module runs three times: with the geometry the library picks for the batch (by average string
+    length), and with each of the two forced (LATOK_B200_GEOMETRY is read at every submit)."""
+    import os
     from latok_b200.engine import Engine
+    old = os.environ.pop("LATOK_B200_GEOMETRY", None)
+    if request.param != "auto":
+        os.environ["LATOK_B200_GEOMETRY"] = request.param
     e = Engine(0)
     yield e
     e.close()
+    os.environ.pop("LATOK_B200_GEOMETRY", None)
+    if old is not None:
+        os.environ["LATOK_B200_GEOMETRY"] = old
 
 
 def check_batch(engine, texts, what=ALL, rules=None, label=""):
@@ -145,7 +156,7 @@ def test_boundary_alignment_sweep(engine):
     # the same patterns against the 1 KB steps inside a range and against the 116-byte closer search windows
     texts = []
     for pat in patterns:
-        for base in (1024, 2048, 3072, 3968 + 116, 3968 + 128, 4096, 2 * 3968 + 116):
+        for base in (1024, 2048, 3072, 3968 + 116, 3968 + 128, 4096, 2 * 3968 + 116, 2944 + 116, 2944 + 128, 2 * 2944 + 116):
             for shift in range(-6, 5):
                 texts.append("q r " + "z" * (base + shift - 8) + " " + pat + " tail end")
     check_batch(engine, texts, label="alignment sweep (steps / search windows)")
@@ -167,7 +178,8 @@ def test_long_space_free_runs_and_walk(engine):
     characters in earlier tiles (latok.c:218-244 has unbounded reach)."""
     cases = []
     for TILE, run in ((7936, 300), (7936, 1000), (7936, 7936 - 50), (7936, 7936 + 300), (7936, 2 * 7936 + 77), (7936, 40000),
-                      (3968, 100), (3968, 130), (3968, 3968 + 300), (35712, 200), (35712, 35712 + 5000), (31744, 200), (3968, 70000)):
+                      (3968, 100), (3968, 130), (3968, 3968 + 300), (35712, 200), (35712, 35712 + 5000), (31744, 200), (3968, 70000),
+                      (2944, 100), (2944, 130), (2944, 2944 + 300), (32384, 200), (32384, 32384 + 5000), (2944, 70000)):
         base = "x y " * ((TILE - 120) // 4)
         cases.append(base + " " + ",".join(["ab"] * (run // 3)) + " end")                    # no mark: commas split
         cases.append(base + " " + ",".join(["ab"] * (run // 3)) + ",q@r end")                # mark at the very end
@@ -283,11 +295,11 @@ def test_backlog_handoff_between_ranges(engine):
     marks = ["aa@bb,cc@dd xx", "aa@bb,cc@dd,ee@ff,gg@hh xx yy zz", "http://a.b/c,x@y,#t d@e.f,g@h uu vv ww",
              "a@b,c@d,e@f,g@h,i@j,k@l,m@n one two three four five six seven"]
     texts = []
-    for shift in range(0, 64, 3):
+    for shift, R in [(sh, R) for R in RANGES for sh in range(0, 64, 3 if R == 3968 else 7)]:
         for m in marks:
             parts, pos = [], 0
-            for k in range(1, 21):                      # one multi-mark chunk near the end of each of 20 ranges (2 tiles + 2)
-                target = 3968 * k - 20 + shift - len(m) // 2
+            for k in range(1, 21 if R == 3968 else 25):  # one multi-mark chunk near the end of each of 20+ ranges (2 tiles + 2)
+                target = R * k - 20 + shift - len(m) // 2
                 pad = max(target - pos, 1)
                 fill = (filler * (pad // len(filler) + 1))[:pad - 1] + " "
                 parts += [fill, m + " "]
