@@ -328,6 +328,12 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     auto Xof = [&](int b) -> uint8_t * { return wbase + (sp.x[b] - sp.warp0); };
     uint32_t *sbmS = reinterpret_cast<uint32_t *>(wbase + (sp.sbm - sp.warp0));
     auto tempof = [&](int b) -> uint32_t * { return reinterpret_cast<uint32_t *>(wbase + (sp.temp[b] - sp.warp0)); };
+    // State words of lane-word (js, ln).  Default rules: the two 16-byte halves of a lane-word's 8 words lie 512 bytes
+    // apart inside the step's 1 KB (word w at js*256 + (w >> 2)*128 + ln*4 + (w & 3)), so the 128-bit accesses of a
+    // quarter warp fall into 32 different banks (a 32-byte lane stride makes them collide in pairs); generic rules: TWG
+    // words in a row.
+    auto SA = [&](uint32_t *base, int js, int ln) -> uint32_t * { return kDefault ? base + js * 256 + ln * 4 : base + (js * 32 + ln) * TWD; };
+    auto SW = [&](int w) -> int { return kDefault ? (w < 4 ? w : 124 + w) : w; };        // offset of word w from SA()
     const uint32_t *lutv = reinterpret_cast<const uint32_t *>(tableS);
 #ifdef LATOK_PROFILE
     long long _prof_t = clock64();
@@ -718,11 +724,11 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 }
                 // ---- park the step for pass C (in place of its input bytes; step js+1 has been read already)
                 {
-                    uint32_t *t = tempS + (js * 32 + lane) * TWD;
+                    uint32_t *t = SA(tempS, js, lane);
                     const uint32_t pk = pack_ncp(n, c0, (int)((LB >> 3) & 1u)) | ((XF & 1u) << 31);
                     if (kDefault) {
                         *reinterpret_cast<uint4 *>(t) = make_uint4(CNT[0], CNT[1], CNT[2], SYC[0]);
-                        *reinterpret_cast<uint4 *>(t + 4) = make_uint4(Sraw, HOTorM, Fm, pk);
+                        *reinterpret_cast<uint4 *>(t + 128) = make_uint4(Sraw, HOTorM, Fm, pk);
                     } else {
 #pragma unroll
                         for (int q = 0; q < NC; ++q) t[q] = CNT[q];
@@ -747,8 +753,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             if (!closed) atomicAdd(&p.result->prof[13], 1ull);
         }
         __syncwarp();
-        auto T_at = [&](int js, int w) -> uint32_t & { return tempS[(js * 32 + lane) * TWD + w]; };
-        (void)T_at;
         // character ends its string: the next character (possibly in the next lane-word) starts one
         auto L_of = [&](uint32_t Fm, uint32_t pk) -> uint32_t {
             const int n = pk_n(pk);
@@ -766,10 +770,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             int lft_max = -1;
 #pragma unroll 1
             for (int js = RS - 1; js >= 0; --js) {
-                uint32_t *t = tempS + (js * 32 + lane) * TWD;
+                uint32_t *t = SA(tempS, js, lane);
                 uint32_t CNT[NC], SYC[NY], Sraw, HOT, Fm, pk;
                 if (kDefault) {
-                    const uint4 a = *reinterpret_cast<const uint4 *>(t), b4 = *reinterpret_cast<const uint4 *>(t + 4);
+                    const uint4 a = *reinterpret_cast<const uint4 *>(t), b4 = *reinterpret_cast<const uint4 *>(t + 128);
                     CNT[0] = a.x; CNT[1] = a.y; CNT[2] = a.z; SYC[0] = a.w; Sraw = b4.x; HOT = b4.y; Fm = b4.z; pk = b4.w;
                 } else {
 #pragma unroll
@@ -836,7 +840,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 const uint32_t leadw = sbmS[js * 32 + lane];      // the window's map is rebuilt by the next analysis: keep the mask here
                 if (kDefault) {
                     *reinterpret_cast<uint4 *>(t) = make_uint4(V[0], V[1], V[2], E);
-                    t[I_H] = leadw; t[I_K] = pk2;
+                    t[SW(I_H)] = leadw; t[SW(I_K)] = pk2;
                 } else {
 #pragma unroll
                     for (int q = 0; q < NV; ++q) t[q] = V[q];
@@ -877,10 +881,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                                       K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens;   // (the direct path checks every pair)
 #pragma unroll 1
         for (int js = 0; js < RS; ++js) {
-            const uint32_t *t = tempS + (js * 32 + lane) * TWD;
+            const uint32_t *t = SA(const_cast<uint32_t *>(tempS), js, lane);
             uint32_t V[NV], E, Sraw, Fm, pk;
             if (kDefault) {
-                const uint4 a = *reinterpret_cast<const uint4 *>(t), b4 = *reinterpret_cast<const uint4 *>(t + 4);
+                const uint4 a = *reinterpret_cast<const uint4 *>(t), b4 = *reinterpret_cast<const uint4 *>(t + 128);
                 V[0] = a.x; V[1] = a.y; V[2] = a.z; E = a.w; Sraw = b4.x; Fm = b4.z; pk = b4.w;
             } else {
 #pragma unroll
@@ -1212,8 +1216,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 if (in) {
                     const int wb = int(o - w0);
                     const int js = wb >> 10, tl = (wb >> 5) & 31;
-                    const uint32_t *t = tempS + (js * 32 + tl) * TWD;
-                    const uint32_t l_pk = t[I_K], l_E = t[I_E], l_lead = t[I_H];
+                    const uint32_t *t = SA(const_cast<uint32_t *>(tempS), js, tl);
+                    const uint32_t l_pk = t[SW(I_K)], l_E = t[SW(I_E)], l_lead = t[SW(I_H)];
                     const int l_c0 = pk_c0(l_pk);
                     const int c = l_c0 + __popc(l_lead & mask_lt_nn(wb & 31));
                     const bool mine = last_range ? (c >= c_lo) : (c >= c_lo && c < c_hi);
