@@ -68,7 +68,7 @@ enum { BAR_AGG = 1, BAR_PRE = 3 };
 static_assert(RANGE == WIN - HALO && HALO % 32 == 0 && RANGE % 16 == 0, "geometry");
 static_assert(TSTAGE >= STEP + 64, "the token stage doubles as the byte stage of partly owned split-mask chunks");
 
-struct WAgg { int n_own, ntok, lft, v, flags, u, mb1, pad; };   // flags: 1 have, 2 closed, 4 lo_found, 8 holds a closer
+struct WAgg { int n_own, ntok, lft, v, flags, u, mb1, pad; };   // flags: 1 have, 2 closed, 4 lo_found, 8 holds a closer, 16 guessed a hot tail
 struct Slot { unsigned long long G, K, base; int mode, pad; };
 struct RInfo { int c_lo, c_hi, n_own, ntok, flags, pad[3]; };    // flags: 1 have, 2 closed, 4 lo_found, 8 last_range
 struct Ctl {
@@ -202,7 +202,11 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 const int src = hl ? 31 - __clz(hl) : 0;
                 const int lv = __shfl_sync(FULL, pn - mn + a.lft, src);
                 lft_rel = hl ? lv : -1;
-                if (first && lane < NW) { su = a.u; sf0 = a.v; smb1 = a.mb1; sflags = a.flags; v_last = a.v; }
+                if (first && lane < NW) {
+                    su = a.u; sf0 = a.v; smb1 = a.mb1; sflags = a.flags; v_last = a.v;
+                    // (what a range that ends inside a chunk guessed in its first analysis)
+                    far_used = (a.flags & 16) ? 1 : 0;
+                }
                 if (!first && again) v_last = a.v;
             };
             // Backlog entering / hot tail of every range, given the backlog `x_tile` that enters the tile; ranges that were
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             // once it has repeated its analysis, and the ranges behind it follow in the next round (rare, short cascades).
             auto resolve = [&](int x_tile) -> int {
                 // nothing enters, nothing is left, every range ends at a closer: almost every tile
-                if (x_tile == 0 && !__any_sync(FULL, lane < NW && (sflags & 1) != 0 && (sf0 != 0 || (sflags & 2) == 0 || x_used != 0 || far_used != 0)))
+                if (x_tile == 0 && !__any_sync(FULL, lane < NW && (sflags & 1) != 0 && (sf0 != 0 || (sflags & 2) == 0 || x_used != 0)))
                     return 0;
                 int x_out = x_tile;
                 for (;;) {
@@ -257,15 +261,27 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                         if (walk) far = any ? 1 : 0;
                         if (lane == 0) atomicAdd(&p.result->walks, 1ull);
                     }
-                    const bool need = have && kin && (xin != x_used || far != far_used);
+                    // the backlog that enters matters where there is a closer to meet it (a range without a summary -- it begins
+                    // at a closer -- is assumed to hold one); a range that lies inside one chunk only needs to know whether
+                    // that chunk will be closed hot
+                    const bool x_matters = (sflags & 4) != 0 || (sflags & 8) != 0;
+                    const bool need = have && kin && ((xin != x_used && x_matters) || far != far_used);
                     if (!__any_sync(FULL, need)) {
                         if (!all_known && lane == 0) atomicOr(&p.result->error, 1u);      // (cannot happen: every round makes a range known)
                         break;
                     }
                     if (lane < NW) { st_vs32(&ctl.patch_x[lane], need ? xin : -1); st_vs32(&ctl.patch_far[lane], far); }
+                    const bool far_changed = need && far != far_used;
                     if (need) { x_used = xin; far_used = far; }
                     again = need;
-                    if (lane == 0) { ctl.slot[s].mode = 2; atomicAdd(&p.result->prof[15], 1ull); }
+                    {   // (statistics: repeat rounds, ranges repeated, of those because of the hot-tail guess)
+                        const unsigned nb = __ballot_sync(FULL, need), fb = __ballot_sync(FULL, far_changed);
+                        if (lane == 0) {
+                            ctl.slot[s].mode = 2;
+                            atomicAdd(&p.result->prof[9], 1ull); atomicAdd(&p.result->prof[8], (unsigned long long)__popc(nb));
+                            atomicAdd(&p.result->prof[7], (unsigned long long)__popc(fb));
+                        }
+                    }
                     __threadfence_block();
                     __syncwarp();
                     nb_arrive(BAR_PRE + s, NTH);
@@ -276,17 +292,24 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             gather(true);
             const long long tile = ld_vs32(&ctl.tile_id[s]);
             if (tile >= p.ntiles) break;
-            // the aggregate is published under the assumption that no backlog enters the tile (true for almost every tile)
-            int v = resolve(0);
-            if (lane == 0) {
-                uint4 r;
-                r.x = (p.epoch << 2) | 1u;
-                r.y = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
-                r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
-                st_rec(p.agg + tile, r);
+            // The aggregate is published under the assumption that no backlog enters the tile (true for almost every tile).
+            // A tile that begins inside a chunk (a long space-free run is passing through) most likely does get one: it
+            // publishes nothing before it knows (its successors would have to wait for its inclusive prefix anyway) and
+            // settles once, with the backlog that really enters.
+            const bool begins_inside = tile > 0 && (__shfl_sync(FULL, sflags, 0) & 5) == 1;
+            int v = 0;
+            if (!begins_inside) {
+                v = resolve(0);
+                if (lane == 0) {
+                    uint4 r;
+                    r.x = (p.epoch << 2) | 1u;
+                    r.y = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
+                    r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
+                    st_rec(p.agg + tile, r);
+                }
             }
             const Prefix pre = lookback(tile, p, lane);
-            if (pre.x != 0) {
+            if (begins_inside || pre.x != 0) {
 #ifdef LATOK_PROFILE
                 const long long _s1 = clock64();
 #endif
@@ -417,12 +440,13 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         return HOT;
     };
     // results of the analysis that are posted right away (the rest goes to ctl.rinfo for pass D)
-    int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0, a_u = 0, a_mb1 = 0, a_flags = 0;
+    int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0, a_u = 0, a_mb1 = 0, a_flags = 0; bool a_guess = false;
 
     // ================================================================================================= analysis
     // x_init: block-mask backlog entering the range; far_init: the chunk open at the end of the range (a range that does
-    // not end at a chunk closer) will be closed hot.  Both are 0 in the first analysis of every range; the service warp
-    // orders a repeat with the real values where they differ (resolve()).
+    // not end at a chunk closer) will be closed hot.  The first analysis of every range assumes that nothing enters and
+    // (far_init = -1) that an open last chunk WILL be closed hot; the service warp orders a repeat with the real values
+    // where that changes the result (resolve()).
     auto analyze = [&](const long long r, const int buf, const int x_init, const int far_init) {
         const long long w0 = r * (long long)RANGE;
         const bool have = r < p.nranges, last_range = r == p.nranges - 1;
@@ -433,9 +457,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         // backlog transfer summary of the owned characters: marks - closers, a string boundary (= reset), marks in front of
         // the first closer, whether there is a closer at all
         int d_mc = 0, mb1 = 0; uint32_t rs_any = 0; bool seen_cl = false;
+        a_guess = false;
         auto finish = [&]() {
             a_n_own = n_own; a_ntok = ntok_range; a_lft = lft >= 0 ? lft - c_lo : -1; a_v = v_out;
-            a_flags = (have ? 1 : 0) | (closed ? 2 : 0) | (lo_found ? 4 : 0) | (seen_cl ? 8 : 0);
+            a_flags = (have ? 1 : 0) | (closed ? 2 : 0) | (lo_found ? 4 : 0) | (seen_cl ? 8 : 0) | (a_guess ? 16 : 0);
             a_u = 0; a_mb1 = 0;
             if (have && !lo_found) {               // (the summary exists)
                 a_u = __any_sync(FULL, rs_any != 0u) ? NEG : __reduce_add_sync(FULL, d_mc);
@@ -762,10 +787,36 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             const bool has_term = (unsigned)(nb_win - (js * STEP + lane * 32)) < 32u;
             return mask_lt(n - (has_term ? 1 : 0));
         };
+        // First analysis of a range that ends inside a chunk: a guess whether that chunk will be closed hot (the service warp
+        // knows better later, resolve()).  Yes if a mark is pending at the end; yes if the range also BEGINS inside the chunk
+        // or the open part is long (a space-free run of that length nearly always holds a mark somewhere); no for a short
+        // open part without a mark (a long word or URL-less stretch at the range end).
+        bool far_guess = false;
+        if (UNLIKELY(!closed)) {
+            far_guess = !lo_found || xb != 0;
+            if (!far_guess) {
+                int open_len = n_own;
+#pragma unroll 1
+                for (int js = RS - 1; js >= 0; --js) {
+                    const uint32_t *t = SA(tempS, js, lane);
+                    const uint32_t pk = t[SW(I_K)];
+                    const int n = pk_n(pk), c0 = pk_c0(pk);
+                    const uint32_t CLo = (t[SW(I_S)] | L_of(t[SW(I_F)], pk)) & range_mask(c0, c_lo, c_hi) & real_mask(js, n);
+                    const unsigned hb = __ballot_sync(FULL, CLo != 0u);
+                    if (hb) {
+                        const int pos = __shfl_sync(FULL, c0 + 31 - (int)__clz(CLo), 31 - __clz(hb));
+                        open_len = c_hi - pos - 1;
+                        break;
+                    }
+                }
+                far_guess = open_len >= 512;
+            }
+        }
+        a_guess = far_init < 0 ? far_guess : (far_init != 0);
         PROF5(2);
         // ---------------------------------------------------------------- pass C: blanked chunks, values, tokens
         {
-            uint32_t bin_step = (uint32_t)far_init;
+            uint32_t bin_step = far_init < 0 ? (far_guess ? 1u : 0u) : (uint32_t)far_init;
             int nsa_carry = -1;
             int lft_max = -1;
 #pragma unroll 1
@@ -1326,7 +1377,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             if (s == 0 ? pending[0] : pending[1]) wait_window(s, phase_bits);
             __syncwarp();
             PROF5(0);
-            analyze((long long)tile_cur * NW + cw, s, 0, 0);
+            analyze((long long)tile_cur * NW + cw, s, 0, -1);
             post(s);
         } else {
             nb_arrive(BAR_AGG + s, NTH);                 // tells the service warp that the tickets have run out
