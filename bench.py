@@ -373,13 +373,13 @@ def measure_resident(cx: Ctx, host, what, steps, warmup, classify, wl_key, sampl
     alg = float(np.mean([b + c + 8 * t + 16 * (s + 1) + (25 * t if classify else 0) for b, c, t, s in stats]))
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else float("nan")
     achieved = alg / (k_ms * 1e-3) / 1e9
-    traffic, traffic_note = None, None
+    traffic, traffic_note, traffic_ratio = None, None, None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
             rec = json.load(open(tf)).get(wl_key)
             if isinstance(rec, dict):
-                traffic, traffic_note = rec.get("dram_bytes"), rec.get("note")
+                traffic, traffic_note, traffic_ratio = rec.get("dram_bytes"), rec.get("note"), rec.get("ratio")
         except Exception:
             pass
     rec = {
@@ -388,7 +388,7 @@ def measure_resident(cx: Ctx, host, what, steps, warmup, classify, wl_key, sampl
         "steps": steps, "ms_per_step": elapsed_ms / steps,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_note": traffic_note,
+                     "traffic": traffic, "traffic_over_algorithmic": traffic_ratio, "traffic_note": traffic_note,
                      "kernel": "latok::v5::tokenize5_kernel<kFeats>" if classify else "latok::v5::tokenize5_kernel",
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
