@@ -69,13 +69,11 @@ static_assert(RANGE == WIN - HALO && HALO % 32 == 0 && RANGE % 16 == 0, "geometr
 static_assert(TSTAGE >= STEP + 64, "the token stage doubles as the byte stage of partly owned split-mask chunks");
 
 struct WAgg { int n_own, ntok, lft, v, flags, u, mb1, pad; };   // flags: 1 have, 2 closed, 4 lo_found, 8 holds a closer, 16 guessed a hot tail
-struct Slot { unsigned long long G, K, base; int mode, pad; };
+struct Slot { unsigned long long G, K, base; int pad[2]; };
 struct RInfo { int c_lo, c_hi, n_own, ntok, flags, pad[3]; };    // flags: 1 have, 2 closed, 4 lo_found, 8 last_range
 struct Ctl {
     int tile_id[2], tk_cnt[2], tk_flag[2];
     int pad0[4];
-    int patch_x[NW];                     // mode 2: backlog with which a range repeats its analysis, -1: not this range
-    int patch_far[NW];                   // ... and whether the chunk open at its end will be closed hot
     Slot slot[2];
     WAgg wagg[2][NW];
     RInfo rinfo[NW][2];
@@ -89,7 +87,7 @@ struct Ctl {
 // the string-start map of the window (bit = byte) turns into the lane-word's lead-byte mask once it has been read and
 // moves into the state in pass C.
 struct Plan {
-    int tables, ctl, mbar, warp0, x[2], sst, tst, sbm, temp[2], per_warp, total;
+    int tables, ctl, mbar, sbm0, warp0, x[2], sst, tst, sbm, temp[2], per_warp, total;
 };
 __host__ __device__ inline Plan plan(const TableLayout &tl, bool is_default)
 {
@@ -98,6 +96,7 @@ __host__ __device__ inline Plan plan(const TableLayout &tl, bool is_default)
     s.tables = take(tl.stage2 - tl.lutv);    // split-value LUT, ASCII / class feature words, stage 1; stage 2 (16 KB) stays in global memory (L1)
     s.ctl = take((int)sizeof(Ctl));
     s.mbar = take(8 * 2 * NW);
+    s.sbm0 = take(RS * 32 * 4);                 // string map of a window the service warp analyses again
     s.warp0 = o;
     s.x[0] = take(XBYTES); s.x[1] = take(XBYTES);
     s.sst = take(SSTAGE);
@@ -176,181 +175,22 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     tb.low_limit = p.tl.low_limit; tb.high_first = p.tl.high_first; tb.high_last = p.tl.high_last; tb.high_feat = p.tl.high_feat;
 
     // =================================================================================================
-    // service warp: tile aggregate, backlog / hot-tail resolution, look-back, prefix hand-down
-    // =================================================================================================
-    if (warp == 0) {
-        for (int k = 0;; ++k) {
-            const int s = k & 1;
-            int n = 0, ntok = 0, lft_rel = -1;
-            // lane i < NW: what range i posted with its FIRST analysis (nothing entering, tail not hot): backlog left (sf0),
-            // flags, and -- only for ranges that begin inside a chunk (flag 4 clear) -- marks - closers (su; NEG: a string
-            // boundary resets the backlog) and the marks in front of the first closer (smb1) ...
-            int su = 0, sf0 = 0, smb1 = 0, sflags = 2 | 4;
-            // ... what it has been analysed with so far, and the backlog it left the last time
-            int x_used = 0, far_used = 0, v_last = 0;
-            bool again = false;                                  // this range took part in the round just gathered
-            auto gather = [&](bool first) {
-                nb_sync(BAR_AGG + s, NTH);
-                const WAgg a = ctl.wagg[s][lane < NW ? lane : 0];
-                const int mn = lane < NW ? a.n_own : 0, mk = lane < NW ? a.ntok : 0;
-                int pn = mn;                                   // inclusive prefix of characters over the ranges
-#pragma unroll
-                for (int d = 1; d < NW; d <<= 1) { const int t = __shfl_up_sync(FULL, pn, d); if (lane >= d) pn += t; }
-                n = __shfl_sync(FULL, pn, NW - 1);
-                ntok = __reduce_add_sync(FULL, mk);
-                const unsigned hl = __ballot_sync(FULL, lane < NW && a.lft >= 0);
-                const int src = hl ? 31 - __clz(hl) : 0;
-                const int lv = __shfl_sync(FULL, pn - mn + a.lft, src);
-                lft_rel = hl ? lv : -1;
-                if (first && lane < NW) {
-                    su = a.u; sf0 = a.v; smb1 = a.mb1; sflags = a.flags; v_last = a.v;
-                    // (what a range that ends inside a chunk guessed in its first analysis)
-                    far_used = (a.flags & 16) ? 1 : 0;
-                }
-                if (!first && again) v_last = a.v;
-            };
-            // Backlog entering / hot tail of every range, given the backlog `x_tile` that enters the tile; ranges that were
-            // analysed with something else repeat their analysis (mode 2), all at once.  Returns the backlog leaving the tile.
-            // A range that begins at a chunk closer has no summary: if a backlog enters it after all, what it leaves is known
-            // once it has repeated its analysis, and the ranges behind it follow in the next round (rare, short cascades).
-            auto resolve = [&](int x_tile) -> int {
-                // nothing enters, nothing is left, every range ends at a closer: almost every tile
-                if (x_tile == 0 && !__any_sync(FULL, lane < NW && (sflags & 1) != 0 && (sf0 != 0 || (sflags & 2) == 0 || x_used != 0)))
-                    return 0;
-                int x_out = x_tile;
-                for (;;) {
-                    int xin = x_tile, x = x_tile, xend = 0;
-                    bool known = true, kin = false, kend = false;    // (x known: entering range i / at its end)
-#pragma unroll 1
-                    for (int i = 0; i < NW; ++i) {
-                        const int ui = __shfl_sync(FULL, su, i), fi = __shfl_sync(FULL, sf0, i), fl = __shfl_sync(FULL, sflags, i);
-                        const int xu = __shfl_sync(FULL, x_used, i), vl = __shfl_sync(FULL, v_last, i);
-                        if (lane == i) { xin = x; kin = known; }
-                        if (known) {
-                            if ((fl & 1) == 0) { /* no data: passes the backlog on */ }
-                            else if ((fl & 4) == 0) x = max(x + ui, fi);
-                            else if (x == 0) x = fi;
-                            else if (x == xu) x = vl;                 // it has been analysed with exactly this backlog
-                            else known = false;
-                        }
-                        if (lane == i) { xend = x; kend = known; }
-                    }
-                    x_out = x;
-                    const bool all_known = known;
-                    const bool have = lane < NW && (sflags & 1) != 0;
-                    const bool open = have && (sflags & 2) == 0;           // the range ends inside a chunk
-                    int far = far_used;
-                    bool walk = false;
-                    {
-                        const unsigned Bm = __ballot_sync(FULL, lane < NW && smb1 > 0), Bc = __ballot_sync(FULL, lane < NW && (sflags & 8) != 0);
-                        const unsigned Bn = __ballot_sync(FULL, lane < NW && (sflags & 1) == 0);
-                        if (open && kend) {
-                            far = 0;
-                            if (xend > 0) far = 1;
-                            else {
-                                // the first later range that holds a mark in front of its first closer / a closer / no data
-                                const unsigned dec = (Bm | Bc | Bn) & (0xFFFFFFFEu << lane) & mask_lt(NW);
-                                if (dec) far = (int)((Bm >> (__ffs(dec) - 1)) & 1u);
-                                else walk = true;                            // the chunk runs on past the end of the tile
-                            }
-                        }
-                    }
-                    if (__any_sync(FULL, walk)) {
-                        const long long tile_w = ld_vs32(&ctl.tile_id[s]);
-                        const bool any = walk_ahead(p, tb, (tile_w + 1) * (long long)NW * RANGE, lane);
-                        if (walk) far = any ? 1 : 0;
-                        if (lane == 0) atomicAdd(&p.result->walks, 1ull);
-                    }
-                    // the backlog that enters matters where there is a closer to meet it (a range without a summary -- it begins
-                    // at a closer -- is assumed to hold one); a range that lies inside one chunk only needs to know whether
-                    // that chunk will be closed hot
-                    const bool x_matters = (sflags & 4) != 0 || (sflags & 8) != 0;
-                    const bool need = have && kin && ((xin != x_used && x_matters) || far != far_used);
-                    if (!__any_sync(FULL, need)) {
-                        if (!all_known && lane == 0) atomicOr(&p.result->error, 1u);      // (cannot happen: every round makes a range known)
-                        break;
-                    }
-                    if (lane < NW) { st_vs32(&ctl.patch_x[lane], need ? xin : -1); st_vs32(&ctl.patch_far[lane], far); }
-                    const bool far_changed = need && far != far_used;
-                    if (need) { x_used = xin; far_used = far; }
-                    again = need;
-                    {   // (statistics: repeat rounds, ranges repeated, of those because of the hot-tail guess)
-                        const unsigned nb = __ballot_sync(FULL, need), fb = __ballot_sync(FULL, far_changed);
-                        if (lane == 0) {
-                            ctl.slot[s].mode = 2;
-                            atomicAdd(&p.result->prof[9], 1ull); atomicAdd(&p.result->prof[8], (unsigned long long)__popc(nb));
-                            atomicAdd(&p.result->prof[7], (unsigned long long)__popc(fb));
-                        }
-                    }
-                    __threadfence_block();
-                    __syncwarp();
-                    nb_arrive(BAR_PRE + s, NTH);
-                    gather(false);
-                }
-                return x_out;
-            };
-            gather(true);
-            const long long tile = ld_vs32(&ctl.tile_id[s]);
-            if (tile >= p.ntiles) break;
-            // The aggregate is published under the assumption that no backlog enters the tile (true for almost every tile).
-            // A tile that begins inside a chunk (a long space-free run is passing through) most likely does get one: it
-            // publishes nothing before it knows (its successors would have to wait for its inclusive prefix anyway) and
-            // settles once, with the backlog that really enters.
-            const bool begins_inside = tile > 0 && (__shfl_sync(FULL, sflags, 0) & 5) == 1;
-            int v = 0;
-            if (!begins_inside) {
-                v = resolve(0);
-                if (lane == 0) {
-                    uint4 r;
-                    r.x = (p.epoch << 2) | 1u;
-                    r.y = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
-                    r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
-                    st_rec(p.agg + tile, r);
-                }
-            }
-            const Prefix pre = lookback(tile, p, lane);
-            if (begins_inside || pre.x != 0) {
-#ifdef LATOK_PROFILE
-                const long long _s1 = clock64();
-#endif
-                v = resolve(pre.x);
-#ifdef LATOK_PROFILE
-                if (lane == 0) { atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
-#endif
-            }
-            if (lane == 0) {
-                IncRec *ir = p.inc + tile;
-                uint4 a, bq;
-                const unsigned long long Gn = pre.G + (unsigned long long)n, Kn = pre.K + (unsigned long long)ntok;
-                const unsigned long long Bn = lft_rel >= 0 ? pre.G + (unsigned long long)lft_rel : pre.base;
-                a.x = (unsigned)Gn; a.y = (unsigned)(Gn >> 32); a.z = (unsigned)Bn; a.w = (unsigned)(Bn >> 32);
-                bq.x = (unsigned)Kn; bq.y = (unsigned)(Kn >> 32); bq.z = (unsigned)v; bq.w = 0;
-                st_rec(ir, a); st_rec(reinterpret_cast<uint4 *>(ir) + 1, bq);
-                __threadfence();
-                uint4 r;
-                r.x = (p.epoch << 2) | 2u;
-                r.y = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
-                r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
-                st_rec(p.agg + tile, r);
-                Slot &sl = ctl.slot[s];
-                sl.G = pre.G; sl.K = pre.K; sl.base = pre.base; sl.mode = 0;
-                __threadfence_block();
-            }
-            __syncwarp();
-            nb_arrive(BAR_PRE + s, NTH);
-        }
-        return;
-    }
-
-    // =================================================================================================
     // compute warps
     // =================================================================================================
-    unsigned char *wbase = smem + sp.warp0 + cw * sp.per_warp;
+    // `tw` = the compute warp whose buffers are worked on: the warp itself, or -- when the service warp repeats the
+    // analysis of a range (resolve()) -- the warp that owns that range
+    int tw = cw;
+    auto wbase_of = [&]() -> unsigned char * { return smem + sp.warp0 + tw * sp.per_warp; };
+    unsigned char *wbase = smem + sp.warp0 + (cw < 0 ? 0 : cw) * sp.per_warp;      // (own buffers: output path of the compute warps)
     uint8_t *sst = wbase + (sp.sst - sp.warp0);
     int2 *tst = reinterpret_cast<int2 *>(wbase + (sp.tst - sp.warp0));
-    auto Xof = [&](int b) -> uint8_t * { return wbase + (sp.x[b] - sp.warp0); };
-    uint32_t *sbmS = reinterpret_cast<uint32_t *>(wbase + (sp.sbm - sp.warp0));
-    auto tempof = [&](int b) -> uint32_t * { return reinterpret_cast<uint32_t *>(wbase + (sp.temp[b] - sp.warp0)); };
+    auto Xof = [&](int b) -> uint8_t * { return wbase_of() + (sp.x[b] - sp.warp0); };
+    // string-start map / lead masks of the window under analysis (the service warp has a scratch of its own: the owner
+    // of the range is busy with its next tile)
+    auto sbm_of = [&]() -> uint32_t * {
+        return reinterpret_cast<uint32_t *>(warp == 0 ? smem + sp.sbm0 : wbase_of() + (sp.sbm - sp.warp0));
+    };
+    auto tempof = [&](int b) -> uint32_t * { return reinterpret_cast<uint32_t *>(wbase_of() + (sp.temp[b] - sp.warp0)); };
     // State words of lane-word (js, ln).  Default rules: the two 16-byte halves of a lane-word's 8 words lie 512 bytes
     // apart inside the step's 1 KB (word w at js*256 + (w >> 2)*128 + ln*4 + (w & 3)), so the 128-bit accesses of a
     // quarter warp fall into 32 different banks (a 32-byte lane stride makes them collide in pairs); generic rules: TWG
@@ -361,7 +201,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
 #ifdef LATOK_PROFILE
     long long _prof_t = clock64();
 #endif
-    for (int i = lane; i < 5 * 36; i += 32) reinterpret_cast<uint32_t *>(sst)[i] = 0;     // bit stage of pass D
+    if (warp != 0) for (int i = lane; i < 5 * 36; i += 32) reinterpret_cast<uint32_t *>(sst)[i] = 0;     // bit stage of pass D
     __syncwarp();
 
     // ---- window load: TMA bulk copy of the 16-byte aligned interior, plain loads for the ragged end
@@ -452,6 +292,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         const bool have = r < p.nranges, last_range = r == p.nranges - 1;
         uint8_t *X = Xof(buf);
         uint32_t *tempS = tempof(buf);
+        uint32_t *sbmS = sbm_of();
         int c_lo = 0, c_hi = CINF, n_own = 0, ntok_range = 0, lft = -1, v_out = 0;
         bool closed = true, lo_found = true;
         // backlog transfer summary of the owned characters: marks - closers, a string boundary (= reset), marks in front of
@@ -467,7 +308,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 a_mb1 = min(__reduce_add_sync(FULL, mb1), 1 << 20);
             }
             if (lane == 0) {
-                RInfo &ri = ctl.rinfo[cw][buf];
+                RInfo &ri = ctl.rinfo[tw][buf];
                 ri.c_lo = c_lo; ri.c_hi = c_hi; ri.n_own = n_own; ri.ntok = ntok_range;
                 ri.flags = (have ? 1 : 0) | (closed ? 2 : 0) | (lo_found ? 4 : 0) | (last_range ? 8 : 0);
             }
@@ -882,7 +723,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 const uint32_t SPq = SPLIT & mask_lt(n) & range_mask(c0, c_lo, closed ? c_hi + 1 : c_hi);
                 const unsigned hs = __ballot_sync(FULL, SPq != 0u);
                 const int firstsp = __shfl_sync(FULL, c0 + __ffs(SPq) - 1, hs ? __ffs(hs) - 1 : 0);
-                if (lane == 0) { ctl.tokstep[cw][buf][js] = tot; ctl.nsa[cw][buf][js] = nsa_carry; }
+                if (lane == 0) { ctl.tokstep[tw][buf][js] = tot; ctl.nsa[tw][buf][js] = nsa_carry; }
                 if (hs) nsa_carry = firstsp;
                 const uint32_t FO = Fm & OWN;
                 if (FO) lft_max = max(lft_max, c0 + 31 - __clz(FO));
@@ -903,6 +744,184 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         finish();
         PROF5(3);
     };
+
+    // =================================================================================================
+    // service warp: tile aggregate, backlog / hot-tail resolution, look-back, prefix hand-down
+    // =================================================================================================
+    if (warp == 0) {
+        for (int k = 0;; ++k) {
+            const int s = k & 1;
+            int n = 0, ntok = 0, lft_rel = -1;
+            // lane i < NW: what range i posted with its FIRST analysis (nothing entering): backlog left (sf0), flags,
+            // and -- only for ranges that begin inside a chunk (flag 4 clear) -- marks - closers (su; NEG: a string
+            // boundary resets the backlog) and the marks in front of the first closer (smb1) ...
+            int su = 0, sf0 = 0, smb1 = 0, sflags = 2 | 4;
+            // ... what it has been analysed with so far, and the backlog it left the last time
+            int x_used = 0, far_used = 0, v_last = 0;
+            // tile totals from what the ranges have posted (ctl.wagg)
+            auto sum_up = [&](bool first) {
+                const WAgg a = ctl.wagg[s][lane < NW ? lane : 0];
+                const int mn = lane < NW ? a.n_own : 0, mk = lane < NW ? a.ntok : 0;
+                int pn = mn;                                   // inclusive prefix of characters over the ranges
+#pragma unroll
+                for (int d = 1; d < NW; d <<= 1) { const int t = __shfl_up_sync(FULL, pn, d); if (lane >= d) pn += t; }
+                n = __shfl_sync(FULL, pn, NW - 1);
+                ntok = __reduce_add_sync(FULL, mk);
+                const unsigned hl = __ballot_sync(FULL, lane < NW && a.lft >= 0);
+                const int src = hl ? 31 - __clz(hl) : 0;
+                const int lv = __shfl_sync(FULL, pn - mn + a.lft, src);
+                lft_rel = hl ? lv : -1;
+                if (first && lane < NW) {
+                    su = a.u; sf0 = a.v; smb1 = a.mb1; sflags = a.flags; v_last = a.v;
+                    far_used = (a.flags & 16) ? 1 : 0;      // (what a range that ends inside a chunk guessed in its first analysis)
+                }
+            };
+            // Backlog entering / hot tail of every range, given the backlog `x_tile` that enters the tile.  A range whose
+            // result depends on something other than what it was analysed with is analysed AGAIN -- by this warp, at once:
+            // the warp that owns the range is busy with its next tile and would only get to it ~10 us later, with the whole
+            // look-back chain waiting (the window is fetched again into the owner's buffer of this tile, which the owner
+            // does not touch before the prefix is handed down; the string map goes to a scratch of the service warp).
+            // A range that begins at a chunk closer has no summary: if a backlog enters it after all, what it leaves is known
+            // once it has been analysed again, and the ranges behind it follow in the next round (rare, short cascades).
+            // Returns the backlog leaving the tile.
+            auto resolve = [&](int x_tile) -> int {
+                // nothing enters, nothing is left, every range ends at a closer: almost every tile
+                if (x_tile == 0 && !__any_sync(FULL, lane < NW && (sflags & 1) != 0 && (sf0 != 0 || (sflags & 2) == 0 || x_used != 0)))
+                    return 0;
+                const long long tile_w = ld_vs32(&ctl.tile_id[s]);
+                int x_out = x_tile;
+                for (;;) {
+                    int xin = x_tile, x = x_tile, xend = 0;
+                    bool known = true, kin = false, kend = false;    // (x known: entering range i / at its end)
+#pragma unroll 1
+                    for (int i = 0; i < NW; ++i) {
+                        const int ui = __shfl_sync(FULL, su, i), fi = __shfl_sync(FULL, sf0, i), fl = __shfl_sync(FULL, sflags, i);
+                        const int xu = __shfl_sync(FULL, x_used, i), vl = __shfl_sync(FULL, v_last, i);
+                        if (lane == i) { xin = x; kin = known; }
+                        if (known) {
+                            if ((fl & 1) == 0) { /* no data: passes the backlog on */ }
+                            else if ((fl & 4) == 0) x = max(x + ui, fi);
+                            else if (x == 0) x = fi;
+                            else if (x == xu) x = vl;                 // it has been analysed with exactly this backlog
+                            else known = false;
+                        }
+                        if (lane == i) { xend = x; kend = known; }
+                    }
+                    x_out = x;
+                    const bool all_known = known;
+                    const bool have = lane < NW && (sflags & 1) != 0;
+                    const bool open = have && (sflags & 2) == 0;           // the range ends inside a chunk
+                    int far = far_used;
+                    bool walk = false;
+                    {
+                        const unsigned Bm = __ballot_sync(FULL, lane < NW && smb1 > 0), Bc = __ballot_sync(FULL, lane < NW && (sflags & 8) != 0);
+                        const unsigned Bn = __ballot_sync(FULL, lane < NW && (sflags & 1) == 0);
+                        if (open && kend) {
+                            far = 0;
+                            if (xend > 0) far = 1;
+                            else {
+                                // the first later range that holds a mark in front of its first closer / a closer / no data
+                                const unsigned dec = (Bm | Bc | Bn) & (0xFFFFFFFEu << lane) & mask_lt(NW);
+                                if (dec) far = (int)((Bm >> (__ffs(dec) - 1)) & 1u);
+                                else walk = true;                            // the chunk runs on past the end of the tile
+                            }
+                        }
+                    }
+                    if (__any_sync(FULL, walk)) {
+                        const bool any = walk_ahead(p, tb, (tile_w + 1) * (long long)NW * RANGE, lane);
+                        if (walk) far = any ? 1 : 0;
+                        if (lane == 0) atomicAdd(&p.result->walks, 1ull);
+                    }
+                    // the backlog that enters matters where there is a closer to meet it (a range without a summary -- it begins
+                    // at a closer -- is assumed to hold one); a range that lies inside one chunk only needs to know whether
+                    // that chunk will be closed hot
+                    const bool x_matters = (sflags & 4) != 0 || (sflags & 8) != 0;
+                    const bool need = have && kin && ((xin != x_used && x_matters) || far != far_used);
+                    unsigned todo = __ballot_sync(FULL, need);
+                    if (!todo) {
+                        if (!all_known && lane == 0) atomicOr(&p.result->error, 1u);      // (cannot happen: every round makes a range known)
+                        break;
+                    }
+                    {   // (statistics: repeat rounds, ranges repeated, of those because of the hot-tail guess)
+                        const unsigned fb = __ballot_sync(FULL, need && far != far_used);
+                        if (lane == 0) {
+                            atomicAdd(&p.result->prof[9], 1ull); atomicAdd(&p.result->prof[8], (unsigned long long)__popc(todo));
+                            atomicAdd(&p.result->prof[7], (unsigned long long)__popc(fb));
+                        }
+                    }
+                    if (need) { x_used = xin; far_used = far; }
+                    while (todo) {
+                        const int i = __ffs(todo) - 1; todo &= todo - 1;
+                        const int xi = __shfl_sync(FULL, xin, i), fi = __shfl_sync(FULL, far, i);
+                        tw = i;
+                        const long long r = tile_w * NW + i;
+                        plain_load(r, s);
+                        analyze(r, s, xi, fi);
+                        if (lane == 0) {                       // (flags and summary stand: they do not depend on what enters)
+                            WAgg &a = ctl.wagg[s][i];
+                            a.n_own = a_n_own; a.ntok = a_ntok; a.lft = a_lft; a.v = a_v;
+                        }
+                        if (lane == i) v_last = a_v;
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    sum_up(false);
+                }
+                return x_out;
+            };
+            nb_sync(BAR_AGG + s, NTH);               // every range of the tile has been analysed and posted
+            sum_up(true);
+            const long long tile = ld_vs32(&ctl.tile_id[s]);
+            if (tile >= p.ntiles) break;
+            // The aggregate is published under the assumption that no backlog enters the tile (true for almost every tile).
+            // A tile that begins inside a chunk (a long space-free run is passing through) most likely does get one: it
+            // publishes nothing before it knows (its successors would have to wait for its inclusive prefix anyway) and
+            // settles once, with the backlog that really enters.
+            const bool begins_inside = tile > 0 && (__shfl_sync(FULL, sflags, 0) & 5) == 1;
+            int v = 0;
+            if (!begins_inside) {
+                v = resolve(0);
+                if (lane == 0) {
+                    uint4 r;
+                    r.x = (p.epoch << 2) | 1u;
+                    r.y = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
+                    r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
+                    st_rec(p.agg + tile, r);
+                }
+            }
+            const Prefix pre = lookback(tile, p, lane);
+            if (begins_inside || pre.x != 0) {
+#ifdef LATOK_PROFILE
+                const long long _s1 = clock64();
+#endif
+                v = resolve(pre.x);
+#ifdef LATOK_PROFILE
+                if (lane == 0) { atomicAdd(&p.result->prof[10], (unsigned long long)(clock64() - _s1)); atomicAdd(&p.result->prof[11], 1ull); }
+#endif
+            }
+            if (lane == 0) {
+                IncRec *ir = p.inc + tile;
+                uint4 a, bq;
+                const unsigned long long Gn = pre.G + (unsigned long long)n, Kn = pre.K + (unsigned long long)ntok;
+                const unsigned long long Bn = lft_rel >= 0 ? pre.G + (unsigned long long)lft_rel : pre.base;
+                a.x = (unsigned)Gn; a.y = (unsigned)(Gn >> 32); a.z = (unsigned)Bn; a.w = (unsigned)(Bn >> 32);
+                bq.x = (unsigned)Kn; bq.y = (unsigned)(Kn >> 32); bq.z = (unsigned)v; bq.w = 0;
+                st_rec(ir, a); st_rec(reinterpret_cast<uint4 *>(ir) + 1, bq);
+                __threadfence();
+                uint4 r;
+                r.x = (p.epoch << 2) | 2u;
+                r.y = (unsigned)n | ((lft_rel >= 0 ? (unsigned)(lft_rel + 1) : 0u) << 16);
+                r.z = (unsigned)ntok | ((unsigned)v << 16); r.w = 0;
+                st_rec(p.agg + tile, r);
+                Slot &sl = ctl.slot[s];
+                sl.G = pre.G; sl.K = pre.K; sl.base = pre.base;
+                __threadfence_block();
+            }
+            __syncwarp();
+            nb_arrive(BAR_PRE + s, NTH);
+        }
+        return;
+    }
 
     // ================================================================================================= output
     auto output = [&](const long long r, const int buf, unsigned long long G_in, unsigned long long K_in, unsigned long long base_in) {
@@ -1326,23 +1345,11 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         }
         phase_bits ^= 1u << b;
     };
-    // write out tile `tile` (iteration kk): wait for its prefix (repeating the analysis if asked to), then pass D
+    // write out tile `tile` (iteration kk): wait for its prefix, then pass D
     auto finish_tile = [&](int tile, int kk) {
         const int s = kk & 1;
         const long long r = (long long)tile * NW + cw;
-        for (;;) {
-            nb_sync(BAR_PRE + s, NTH);
-            const int mode = ctl.slot[s].mode;
-            if (mode == 0) break;
-            // mode 2: a backlog enters this range after all, or the chunk open at its end will be closed hot -- its ordinary
-            // analysis once more, with them (the other ranges of the tile just answer; what they posted stands).
-            // (ONE more call site only: every inlined copy of the analysis costs the regular path instruction-cache misses)
-            const int px = ld_vs32(&ctl.patch_x[cw]), pfar = ld_vs32(&ctl.patch_far[cw]);
-            if (px < 0 || r >= p.nranges) { nb_arrive(BAR_AGG + s, NTH); continue; }
-            plain_load(r, s);
-            analyze(r, s, px, pfar);
-            post(s);
-        }
+        nb_sync(BAR_PRE + s, NTH);
         PROF5(4);
         // own prefix: the tile's plus the ranges before this one
         unsigned long long G_in, K_in, base_in;
