@@ -24,8 +24,9 @@
 // closer and whether it begins / ends at a chunk closer.  The service warp composes these over the ranges of the tile:
 // the backlog that really enters every range (several marks in a chunk, a backlog from the previous tile) and, for a
 // range that ends inside a chunk (a space-free run longer than the search windows), whether that chunk's closer will be
-// hot (a pending mark, a mark in a later range, or -- past the end of the tile -- the look-ahead walk).  The ranges whose
-// (backlog, hot tail) differ from what they assumed (0, 0) repeat their ORDINARY analysis with them, all at once.
+// hot (a pending mark, a mark in a later range, or -- past the end of the tile -- the look-ahead walk).  A range whose
+// result depends on something it assumed differently is analysed again (the ORDINARY analysis, with the real values) by
+// the service warp itself, at once: the warp that owns the range is busy with its next tile by then.
 // The warps run one tile ahead of the look-back: analysis of tile k+1, then pass D of tile k, whose state waits in
 // place of its input bytes (two window buffers per warp).  Tickets are taken by the first warp that is ready for the
 // next tile, so ticket order follows start order and predecessors publish first.
