@@ -31,6 +31,19 @@ LATOK_HD uint32_t bits_byte_perm(uint32_t a, uint32_t b, uint32_t sel)
 #endif
 }
 
+// (a & M) | (b & ~M) for a constant mask M
+template <uint32_t M>
+LATOK_HD uint32_t bits_select(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__) && !defined(LATOK_NO_LOP3_ASM)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(a), "r"(b), "n"(M));     // c ? a : b
+    return r;
+#else
+    return (a & M) | (b & ~M);
+#endif
+}
+
 // 32 bytes (w[i] = bytes 4i..4i+3, little endian) -> 8 bit-planes: bit j of b[k] = bit k of byte j.
 // Step 1: two 4x4 byte transposes put byte (8q + r) into byte q of word r, so that bit position 8q + r' of
 // register k after the 8x8 bit transpose (three delta-swap stages between register pairs) is character 8q + r'.
@@ -50,10 +63,11 @@ LATOK_HD void bytes_to_planes(const uint32_t w[8], uint32_t b[8])
         u[6] = bits_byte_perm(t1, t3, 0x5410); u[7] = bits_byte_perm(t1, t3, 0x7632);
     }
     // 8x8 bit transpose inside every byte column: element (register r, bit k) <-> (register k, bit r)
+    // (bits_select: one LOP3 per half of a swap -- the compiler's own lowering of the masked form takes two)
 #define LATOK_SWAP(i, j, s, m)                                       \
     {                                                                \
-        const uint32_t lo = (u[i] & (m)) | ((u[j] << (s)) & ~(m));   \
-        const uint32_t hi = ((u[i] >> (s)) & (m)) | (u[j] & ~(m));   \
+        const uint32_t lo = bits_select<(m)>(u[i], u[j] << (s));     \
+        const uint32_t hi = bits_select<(m)>(u[i] >> (s), u[j]);     \
         u[i] = lo; u[j] = hi;                                        \
     }
     LATOK_SWAP(0, 4, 4, 0x0F0F0F0Fu) LATOK_SWAP(1, 5, 4, 0x0F0F0F0Fu) LATOK_SWAP(2, 6, 4, 0x0F0F0F0Fu) LATOK_SWAP(3, 7, 4, 0x0F0F0F0Fu)

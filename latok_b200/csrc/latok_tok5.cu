@@ -368,7 +368,11 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         int crun = 0;                    // characters of the range so far
         int xb = x_init;                 // block-mask backlog entering the next step (regular evaluation; 0 almost always)
 
+#ifdef LATOK_V5_UNROLL_A
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (int j = 0; j <= RS; ++j) {
             // -------------------------------------------------------------- base planes of step j
             uint32_t Pc[NBASE], Fc = 0, leadc = 0; int nc = 0, c0c = 0;
@@ -948,6 +952,17 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         int ktok = 0;                      // tokens of the range before this step
         unsigned fc[7] = {0, 0, 0, 0, 0, 0, 0};      // token-feature mode: sums of the token open at the end of the previous step
         bool fc_hit = false;                          // ... and whether its first character has been seen
+        // token-feature rows: aligned base of the rows of this range, byte phase of relative row 0 in it, the relative
+        // ordinals that may be written ([f_kmin, f_kmax): row capacity of the caller's array)
+        uint32_t *f_base = nullptr; int f_phase = 0, f_kmin = 0, f_kmax = 0;
+        if (kFeats) {
+            const unsigned long long fb = K_in * (unsigned long long)NFEAT;
+            f_phase = (int)(fb & 3ull);
+            f_base = reinterpret_cast<uint32_t *>(p.feats + (fb - (unsigned long long)f_phase));
+            f_kmin = K_in > 0ull ? -1 : 0;
+            const long long room = p.cap_tokens - (long long)K_in;
+            f_kmax = room > (long long)(1 << 28) ? (1 << 28) : (room < -1 ? -1 : (int)room);
+        }
         const bool spans_direct_all = !closed || !lo_found ||
                                       K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens;   // (the direct path checks every pair)
 #pragma unroll 1
@@ -1158,11 +1173,12 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     __syncwarp();
                     int2 *gb = reinterpret_cast<int2 *>(p.spans) + (Ks - (unsigned long long)ka);
                     const int tot = ka + ntok_step;
-                    for (int j = 2 * lane; j < tot; j += 64) {
-                        if (j >= ka && j + 1 < tot) *reinterpret_cast<uint4 *>(gb + j) = *reinterpret_cast<const uint4 *>(tst + j);
-                        else if (j >= ka) gb[j] = tst[j];
-                        else if (j + 1 < tot) gb[j + 1] = tst[j + 1];
-                    }
+                    // whole chunks: slots 2c, 2c + 1 for c in [ka, tot / 2); the two single pairs at the ends by lane 0 / 1
+                    const int cend = tot >> 1;
+                    for (int c = ka + lane; c < cend; c += 32)
+                        *reinterpret_cast<uint4 *>(gb + 2 * c) = *reinterpret_cast<const uint4 *>(tst + 2 * c);
+                    if (lane == 0 && ka != 0 && tot > 1) gb[1] = tst[1];
+                    if (lane == 1 && (tot & 1) != 0 && tot - 1 >= ka) gb[tot - 1] = tst[tot - 1];
                     __syncwarp();
                 }
             }
@@ -1222,30 +1238,51 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     }
                 };
                 {
+                    // The token ends of a lane-word close tokens with consecutive ordinals, so the lane's rows are ONE byte
+                    // stream of the [T, 25] array: it goes out as whole aligned words (the bytes of a row that do not fill a
+                    // word wait in `carry` for the next row), and only the bytes that share a word with a row of another
+                    // lane -- in front of the lane's first row and behind its last one -- are stored singly.
                     const uint32_t PSr = (Sraw << 1) | pk_ps(pk);
                     uint32_t ev = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo + 1, c_hi + 1);
-                    while (ev) {
-                        const int i = __ffs(ev) - 1; ev &= ev - 1;
-                        const long long k = (long long)K_in + ktok + tp + __popc(E & mask_lt_nn(i)) - 1;
-                        if (k < 0 || k >= p.cap_tokens) continue;
-                        unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0};
-                        const uint32_t below = SPLIT & mask_lt_nn(i);
-                        bool hit = below != 0u;
-                        plane_sums(mask_lt_nn(i) & ~mask_lt_nn(hit ? 31 - __clz(below) : 0), acc);
-                        if (!hit) walk_lanes(lane - 1, acc, hit);
-                        // the 25-byte row starts at byte 25 k: whole words where they are ours alone, single bytes at the ends
-                        int8_t *row = p.feats + k * NFEAT;
-                        const int head = (int)((0u - (unsigned)(k & 3)) & 3u);
-                        auto put = [&](int hb) {
-                            for (int q = 0; q < hb; ++q) row[q] = (int8_t)((acc[0] >> (8 * q)) & 0xFFu);
-                            const int nw = (NFEAT - hb) >> 2;
-                            uint32_t *w = reinterpret_cast<uint32_t *>(row + hb);
-#pragma unroll
-                            for (int j = 0; j < 6; ++j)
-                                if (j < nw) w[j] = hb ? __funnelshift_r(acc[j], acc[j + 1], 8 * hb) : acc[j];
-                            for (int q = hb + 4 * nw; q < NFEAT; ++q) row[q] = (int8_t)((acc[q >> 2] >> (8 * (q & 3))) & 0xFFu);
-                        };
-                        if (head == 0) put(0); else if (head == 1) put(1); else if (head == 2) put(2); else put(3);
+                    if (ev) {
+                        // ordinal of the first row, relative to the first token of the range (-1: the token began in an earlier range)
+                        int kr = ktok + tp + __popc(E & mask_lt_nn(__ffs(ev) - 1)) - 1;
+                        if (kr < f_kmin) { ev &= ev - 1; ++kr; }                      // (no token in front of it at all)
+                        int o = f_phase + NFEAT * kr;                                   // byte offset of the row from the aligned base
+                        int cnt = o & 3, wo = o >> 2;                                   // bytes waiting in `carry`; next whole word
+                        uint32_t carry = 0;
+                        bool first = true;
+                        while (ev && kr < f_kmax) {
+                            const int i = __ffs(ev) - 1; ev &= ev - 1;
+                            unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0};
+                            const uint32_t below = SPLIT & mask_lt_nn(i);
+                            bool hit = below != 0u;
+                            plane_sums(mask_lt_nn(i) & ~mask_lt_nn(hit ? 31 - __clz(below) : 0), acc);
+                            if (!hit) walk_lanes(lane - 1, acc, hit);
+                            const uint32_t S = 8u * (uint32_t)cnt;
+                            const uint32_t o0 = carry | (acc[0] << S);
+                            const uint32_t o1 = __funnelshift_l(acc[0], acc[1], S), o2 = __funnelshift_l(acc[1], acc[2], S);
+                            const uint32_t o3 = __funnelshift_l(acc[2], acc[3], S), o4 = __funnelshift_l(acc[3], acc[4], S);
+                            const uint32_t o5 = __funnelshift_l(acc[4], acc[5], S), o6 = __funnelshift_l(acc[5], acc[6], S);
+                            uint32_t *w = f_base + wo;
+                            if (first && cnt) {                  // the low bytes of this word belong to the row before
+                                uint8_t *b = reinterpret_cast<uint8_t *>(w);
+                                if (cnt <= 1) b[1] = (uint8_t)(o0 >> 8);
+                                if (cnt <= 2) b[2] = (uint8_t)(o0 >> 16);
+                                b[3] = (uint8_t)(o0 >> 24);
+                            } else w[0] = o0;
+                            w[1] = o1; w[2] = o2; w[3] = o3; w[4] = o4; w[5] = o5;
+                            if (cnt == 3) { w[6] = o6; carry = 0; wo += 7; } else { carry = o6; wo += 6; }
+                            cnt = (cnt + 1) & 3;
+                            first = false;
+                            ++kr;
+                        }
+                        if (!first && cnt) {                     // the last bytes share their word with the next row
+                            uint8_t *b = reinterpret_cast<uint8_t *>(f_base + wo);
+                            b[0] = (uint8_t)carry;
+                            if (cnt >= 2) b[1] = (uint8_t)(carry >> 8);
+                            if (cnt == 3) b[2] = (uint8_t)(carry >> 16);
+                        }
                     }
                 }
                 // the token open at the end of this step, for the steps after it (the same walk from the last lane, by all)
