@@ -64,10 +64,13 @@ constexpr int XBYTES = LPAD + WIN + 16;
 constexpr int SSTAGE = 5 * 36 * 4;          // pass D: bit stage (up to 5 value planes, 36 words each)
 constexpr int TCAP = 320;                // tokens staged per step; steps with more write their pairs directly
 constexpr int TSTAGE = (TCAP + 2) * 8;
+constexpr int FLIST = 512;               // token-feature mode: token ends per step that are written in the order of their ordinals
+constexpr int FSTAGE = 832;              // ... row stage of one trip: 15 + 32 * 25 bytes, in 16-byte chunks
 constexpr int TWG = 12;                  // generic rules: words per lane-word in the (separate) state buffers
 enum { BAR_AGG = 1, BAR_PRE = 3 };
 static_assert(RANGE == WIN - HALO && HALO % 32 == 0 && RANGE % 16 == 0, "geometry");
 static_assert(TSTAGE >= STEP + 64, "the token stage doubles as the byte stage of partly owned split-mask chunks");
+static_assert(TSTAGE >= 1024 + FSTAGE && FSTAGE >= 15 + 32 * NFEAT + 8 && FSTAGE % 16 == 0, "token-feature mode: tails + row stage live in the token stage");
 
 struct WAgg { int n_own, ntok, lft, v, flags, u, mb1, pad; };   // flags: 1 have, 2 closed, 4 lo_found, 8 holds a closer, 16 guessed a hot tail
 struct Slot { unsigned long long G, K, base; int pad[2]; };
@@ -954,9 +957,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         bool fc_hit = false;                          // ... and whether its first character has been seen
         // token-feature rows: aligned base of the rows of this range, byte phase of relative row 0 in it, the relative
         // ordinals that may be written ([f_kmin, f_kmax): row capacity of the caller's array)
-        uint32_t *f_base = nullptr; int f_phase = 0, f_kmin = 0, f_kmax = 0;
+        uint32_t *f_base = nullptr; int f_phase = 0, f_kmin = 0, f_kmax = 0; unsigned long long f_off = 0;
         if (kFeats) {
             const unsigned long long fb = K_in * (unsigned long long)NFEAT;
+            f_off = fb;
             f_phase = (int)(fb & 3ull);
             f_base = reinterpret_cast<uint32_t *>(p.feats + (fb - (unsigned long long)f_phase));
             f_kmin = K_in > 0ull ? -1 : 0;
@@ -965,6 +969,33 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         }
         const bool spans_direct_all = !closed || !lo_found ||
                                       K_in + (unsigned long long)ntok_range > (unsigned long long)p.cap_tokens;   // (the direct path checks every pair)
+        // ---------------------------------------------------------------- CSR offsets of the strings that start in this range
+        // (first: in token-feature mode the step loop below reuses the state of a step, once read, as scratch)
+        // (one lane per string; the character / token counts in front of a byte position come from the parked state)
+        {
+            __syncwarp();
+            const long long wend = w0 + WIN;
+            for (long long q = p.tile_first_str[r] + lane;; q += 32) {
+                const long long o = q <= p.n_strings ? p.offsets[q] : 0x7FFFFFFFFFFFFFFFLL;
+                const bool in = o < wend;
+                if (in) {
+                    const int wb = int(o - w0);
+                    const int js = wb >> 10, tl = (wb >> 5) & 31;
+                    const uint32_t *t = SA(const_cast<uint32_t *>(tempS), js, tl);
+                    const uint32_t l_pk = t[SW(I_K)], l_E = t[SW(I_E)], l_lead = t[SW(I_H)];
+                    const int l_c0 = pk_c0(l_pk);
+                    const int c = l_c0 + __popc(l_lead & mask_lt_nn(wb & 31));
+                    const bool mine = last_range ? (c >= c_lo) : (c >= c_lo && c < c_hi);
+                    if (mine) {
+                        int kb = 0;
+                        for (int q2 = 0; q2 < js; ++q2) kb += ctl.tokstep[cw][buf][q2];
+                        p.char_off[q] = (long long)(G_in + (unsigned long long)(c - c_lo));
+                        p.tok_off[q] = (long long)K_in + kb + pk_tp(l_pk) + __popc(l_E & mask_lt(c - l_c0));
+                    }
+                }
+                if (!__all_sync(FULL, in)) break;
+            }
+        }
 #pragma unroll 1
         for (int js = 0; js < RS; ++js) {
             const uint32_t *t = SA(const_cast<uint32_t *>(tempS), js, lane);
@@ -1238,12 +1269,83 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     }
                 };
                 {
-                    // The token ends of a lane-word close tokens with consecutive ordinals, so the lane's rows are ONE byte
-                    // stream of the [T, 25] array: it goes out as whole aligned words (the bytes of a row that do not fill a
-                    // word wait in `carry` for the next row), and only the bytes that share a word with a row of another
-                    // lane -- in front of the lane's first row and behind its last one -- are stored singly.
+                    // Every token end (a split that follows a non-space character) closes the token with the next ordinal, so
+                    // the token ends of a step are rows kr0 .. kr0 + nrows - 1 of the [T, 25] array, in the order of the lanes.
                     const uint32_t PSr = (Sraw << 1) | pk_ps(pk);
                     uint32_t ev = SPLIT & ~PSr & mask_lt(n) & range_mask(c0, c_lo + 1, c_hi + 1);
+                    // ordinal of the lane's first row, relative to the first token of the range (-1: the token began in an earlier range)
+                    const int kr_first = ev ? ktok + tp + __popc(E & mask_lt_nn(__ffs(ev) - 1)) - 1 : 0;
+                    const unsigned has_ev = __ballot_sync(FULL, ev != 0u);
+                    const int kr0 = __shfl_sync(FULL, kr_first, has_ev ? __ffs(has_ev) - 1 : 0);
+                    const int nrows = has_ev ? __shfl_sync(FULL, kr_first + __popc(ev) - 1, 31 - __clz(has_ev)) - kr0 + 1 : 0;
+                    if (nrows > 0 && nrows <= FLIST) {
+                        // Rows in the order of their ordinals, 32 per trip, one per lane -- whatever lane-word a token ended in
+                        // (the lane-words of a warp hold between none and a dozen token ends: a loop of every lane over its own
+                        // ones runs as long as the busiest lane, and its rows would leave the warp as scattered words).
+                        // (1) every lane lists its token ends: lane-word, position, position of the split the token began at
+                        uint16_t *list = reinterpret_cast<uint16_t *>(SA(const_cast<uint32_t *>(tempS), js, 0));   // (the step's state has been read)
+                        {
+                            uint32_t e = ev; int idx = kr_first - kr0;
+                            while (e) {
+                                const int i = __ffs(e) - 1; e &= e - 1;
+                                const uint32_t below = SPLIT & mask_lt_nn(i);
+                                const uint32_t st = below ? (uint32_t)(31 - __clz(below)) : 0u;
+                                list[idx++] = (uint16_t)((uint32_t)lane | ((uint32_t)i << 5) | (st << 10) | (below ? 0x8000u : 0u));
+                            }
+                        }
+                        uint8_t *rst = reinterpret_cast<uint8_t *>(tst) + 1024;            // row stage: 15 + 32 * 25 bytes, behind the tails
+                        for (int c = lane; c < FSTAGE / 16; c += 32) *reinterpret_cast<uint4 *>(rst + 16 * c) = make_uint4(0, 0, 0, 0);
+                        __syncwarp();
+                        // (2) the rows that may be written (row capacity of the caller's array; no row in front of the first token)
+                        const int jlo = max(0, f_kmin - kr0), jhi = min(nrows, f_kmax - kr0);
+                        for (int jb = jlo; jb < jhi; jb += 32) {
+                            const int j = jb + lane;
+                            const bool valid = j < jhi;
+                            const uint32_t rec = valid ? (uint32_t)list[j] : (uint32_t)lane;
+                            const int w = (int)(rec & 31u), i = (int)((rec >> 5) & 31u), st = (int)((rec >> 10) & 31u);
+                            bool hit = (rec & 0x8000u) != 0u;
+                            const uint32_t frag = valid ? (mask_lt_nn(i) & ~mask_lt_nn(st)) : 0u;
+                            unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                            for (int f = 0; f < NFEAT; ++f)
+                                acc[f >> 2] += (unsigned)__popc(__shfl_sync(FULL, Q[f], w) & frag) << (8 * (f & 3));
+                            if (valid && !hit) walk_lanes(w - 1, acc, hit);
+                            // (3) the 32 rows are consecutive bytes of the array: staged at their byte phase inside a 16-byte
+                            // chunk, they leave as whole chunks; the bytes of the first and the last chunk that belong to this
+                            // trip go singly (their neighbours are written by another trip / step / warp)
+                            const unsigned long long gbyte = f_off + (unsigned long long)((long long)NFEAT * (kr0 + jb));   // first byte of the trip's rows
+                            const int sp0 = (int)(gbyte & 15ull);
+                            const int nv = min(32, jhi - jb), send = sp0 + NFEAT * nv;
+                            if (valid) {
+                                const int pb = sp0 + NFEAT * lane;
+                                const uint32_t S = 8u * (uint32_t)(pb & 3);
+                                uint32_t *wq = reinterpret_cast<uint32_t *>(rst) + (pb >> 2);
+                                atomicOr(wq, acc[0] << S);                                   // (shares its word with the row before)
+                                wq[1] = __funnelshift_l(acc[0], acc[1], S); wq[2] = __funnelshift_l(acc[1], acc[2], S);
+                                wq[3] = __funnelshift_l(acc[2], acc[3], S); wq[4] = __funnelshift_l(acc[3], acc[4], S);
+                                wq[5] = __funnelshift_l(acc[4], acc[5], S);
+                                atomicOr(wq + 6, __funnelshift_l(acc[5], acc[6], S));       // (... with the row after)
+                            }
+                            __syncwarp();
+                            int8_t *g0 = p.feats + (gbyte - (unsigned long long)sp0);        // 16-byte aligned
+                            const int e0 = send & ~15;
+                            if (lane < 16) {
+                                if (sp0 > 0 && lane >= sp0 && lane < send) g0[lane] = (int8_t)rst[lane];
+                                if ((e0 > 0 || sp0 == 0) && e0 + lane < send) g0[e0 + lane] = (int8_t)rst[e0 + lane];
+                            }
+                            __syncwarp();
+                            const int c0f = sp0 > 0 ? 1 : 0, c1f = send >> 4, nch = (send + 15) >> 4;
+                            for (int c = lane; c < nch; c += 32) {
+                                const uint4 v = *reinterpret_cast<const uint4 *>(rst + 16 * c);
+                                *reinterpret_cast<uint4 *>(rst + 16 * c) = make_uint4(0, 0, 0, 0);
+                                if (c >= c0f && c < c1f) *reinterpret_cast<uint4 *>(g0 + 16 * c) = v;
+                            }
+                            __syncwarp();
+                        }
+                    } else if (nrows > 0) {
+                    // (more token ends in one step than the list holds: every lane writes the rows of its own token ends as one
+                    // byte stream -- whole aligned words, the bytes of a row that do not fill a word wait in `carry` for the
+                    // next row, the bytes that share a word with a row of another lane go singly)
                     if (ev) {
                         // ordinal of the first row, relative to the first token of the range (-1: the token began in an earlier range)
                         int kr = ktok + tp + __popc(E & mask_lt_nn(__ffs(ev) - 1)) - 1;
@@ -1284,6 +1386,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                             if (cnt == 3) b[2] = (uint8_t)(carry >> 16);
                         }
                     }
+                    }
                 }
                 // the token open at the end of this step, for the steps after it (the same walk from the last lane, by all)
                 {
@@ -1311,32 +1414,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 st_rec(o + 2, make_uint4(fc[4], fc[5], fc[6], 0u));
                 __threadfence();
                 st_rec(o, make_uint4(fc_hit ? 1u : 0u, p.epoch, 0u, 0u));
-            }
-        }
-        // ---------------------------------------------------------------- CSR offsets of the strings that start in this range
-        // (one lane per string; the character / token counts in front of a byte position come from the parked state)
-        {
-            __syncwarp();
-            const long long wend = w0 + WIN;
-            for (long long q = p.tile_first_str[r] + lane;; q += 32) {
-                const long long o = q <= p.n_strings ? p.offsets[q] : 0x7FFFFFFFFFFFFFFFLL;
-                const bool in = o < wend;
-                if (in) {
-                    const int wb = int(o - w0);
-                    const int js = wb >> 10, tl = (wb >> 5) & 31;
-                    const uint32_t *t = SA(const_cast<uint32_t *>(tempS), js, tl);
-                    const uint32_t l_pk = t[SW(I_K)], l_E = t[SW(I_E)], l_lead = t[SW(I_H)];
-                    const int l_c0 = pk_c0(l_pk);
-                    const int c = l_c0 + __popc(l_lead & mask_lt_nn(wb & 31));
-                    const bool mine = last_range ? (c >= c_lo) : (c >= c_lo && c < c_hi);
-                    if (mine) {
-                        int kb = 0;
-                        for (int q2 = 0; q2 < js; ++q2) kb += ctl.tokstep[cw][buf][q2];
-                        p.char_off[q] = (long long)(G_in + (unsigned long long)(c - c_lo));
-                        p.tok_off[q] = (long long)K_in + kb + pk_tp(l_pk) + __popc(l_E & mask_lt(c - l_c0));
-                    }
-                }
-                if (!__all_sync(FULL, in)) break;
             }
         }
         if (last_range && lane == 0) {
