@@ -283,6 +283,25 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         if (xin != 0 || Mm) out = eval_backlog(xin, Mm, FmA, S, Lm, HOT);
         return HOT;
     };
+    // ---- string-start map of a window (bit = byte position), from the offsets of the strings that begin in it.  Needs
+    // nothing of the window itself: the compute warps build it while the window is still on its way (the two dependent
+    // global loads overlap the TMA copy).
+    auto build_map = [&](const long long r) {
+        if (r >= p.nranges) return;
+        uint32_t *sbmS = sbm_of();
+        const long long w0 = r * (long long)RANGE;
+#pragma unroll
+        for (int j = 0; j < RS; ++j) sbmS[j * 32 + lane] = 0;
+        __syncwarp();
+        const long long wend = w0 + WIN;
+        for (long long s = p.tile_first_str[r] + lane; s <= p.n_strings; s += 32) {
+            const long long o = p.offsets[s];
+            if (o >= wend) break;
+            const int wb = int(o - w0);
+            atomicOr(&sbmS[wb >> 5], 1u << (wb & 31));
+        }
+        __syncwarp();
+    };
     // results of the analysis that are posted right away (the rest goes to ctl.rinfo for pass D)
     int a_n_own = 0, a_ntok = 0, a_lft = -1, a_v = 0, a_u = 0, a_mb1 = 0, a_flags = 0; bool a_guess = false;
 
@@ -323,20 +342,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
             v_out = x_init;
             finish();
             return;
-        }
-        // ---- string-start map of the window (bit = byte position), from the offsets of the strings that begin in it
-        {
-#pragma unroll
-            for (int j = 0; j < RS; ++j) sbmS[j * 32 + lane] = 0;
-            __syncwarp();
-            const long long wend = w0 + WIN;
-            for (long long s = p.tile_first_str[r] + lane; s <= p.n_strings; s += 32) {
-                const long long o = p.offsets[s];
-                if (o >= wend) break;
-                const int wb = int(o - w0);
-                atomicOr(&sbmS[wb >> 5], 1u << (wb & 31));
-            }
-            __syncwarp();
         }
         // ---- the character in front of the window: prev-context of the window's first character.  Matters only when the
         // range owns that character, i.e. no closer is found in the head window (then the range begins inside a chunk), and
@@ -864,6 +869,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                         tw = i;
                         const long long r = tile_w * NW + i;
                         plain_load(r, s);
+                        build_map(r);
                         analyze(r, s, xi, fi);
                         if (lane == 0) {                       // (flags and summary stand: they do not depend on what enters)
                             WAgg &a = ctl.wagg[s][i];
@@ -957,10 +963,11 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         bool fc_hit = false;                          // ... and whether its first character has been seen
         // token-feature rows: aligned base of the rows of this range, byte phase of relative row 0 in it, the relative
         // ordinals that may be written ([f_kmin, f_kmax): row capacity of the caller's array)
-        uint32_t *f_base = nullptr; int f_phase = 0, f_kmin = 0, f_kmax = 0; unsigned long long f_off = 0;
+        uint32_t *f_base = nullptr; int f_phase = 0, f_kmin = 0, f_kmax = 0, f_ph16 = 0; int8_t *f_g16 = nullptr;
         if (kFeats) {
             const unsigned long long fb = K_in * (unsigned long long)NFEAT;
-            f_off = fb;
+            f_ph16 = (int)(fb & 15ull);
+            f_g16 = p.feats + (fb - (unsigned long long)f_ph16);
             f_phase = (int)(fb & 3ull);
             f_base = reinterpret_cast<uint32_t *>(p.feats + (fb - (unsigned long long)f_phase));
             f_kmin = K_in > 0ull ? -1 : 0;
@@ -1239,9 +1246,13 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     *reinterpret_cast<uint4 *>(tailsS + lane * 8 + 4) = make_uint4(tl[4], tl[5], tl[6], SPw ? 1u : 0u);
                 }
                 __syncwarp();
+                // four uint8 additions with wrap-around (latok.c:342-354 sums in uint8) in five instructions; __vadd4 takes ten
+                auto vadd = [](unsigned x, unsigned y) -> unsigned {
+                    return ((x & 0x7F7F7F7Fu) + (y & 0x7F7F7F7Fu)) ^ ((x ^ y) & 0x80808080u);
+                };
                 auto add8 = [&](unsigned acc[7], const uint4 &a, const uint4 &b) {
-                    acc[0] = __vadd4(acc[0], a.x); acc[1] = __vadd4(acc[1], a.y); acc[2] = __vadd4(acc[2], a.z); acc[3] = __vadd4(acc[3], a.w);
-                    acc[4] = __vadd4(acc[4], b.x); acc[5] = __vadd4(acc[5], b.y); acc[6] = __vadd4(acc[6], b.z);
+                    acc[0] = vadd(acc[0], a.x); acc[1] = vadd(acc[1], a.y); acc[2] = vadd(acc[2], a.z); acc[3] = vadd(acc[3], a.w);
+                    acc[4] = vadd(acc[4], b.x); acc[5] = vadd(acc[5], b.y); acc[6] = vadd(acc[6], b.z);
                 };
                 // open tails of the lanes below `t`, then of the steps before (fc*), then of the ranges before (osum chain)
                 auto walk_lanes = [&](int t, unsigned acc[7], bool &hit) {
@@ -1313,8 +1324,8 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                             // (3) the 32 rows are consecutive bytes of the array: staged at their byte phase inside a 16-byte
                             // chunk, they leave as whole chunks; the bytes of the first and the last chunk that belong to this
                             // trip go singly (their neighbours are written by another trip / step / warp)
-                            const unsigned long long gbyte = f_off + (unsigned long long)((long long)NFEAT * (kr0 + jb));   // first byte of the trip's rows
-                            const int sp0 = (int)(gbyte & 15ull);
+                            const int rb = f_ph16 + NFEAT * (kr0 + jb);                     // first byte of the trip's rows, from f_g16
+                            const int sp0 = rb & 15;
                             const int nv = min(32, jhi - jb), send = sp0 + NFEAT * nv;
                             if (valid) {
                                 const int pb = sp0 + NFEAT * lane;
@@ -1327,18 +1338,24 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                                 atomicOr(wq + 6, __funnelshift_l(acc[5], acc[6], S));       // (... with the row after)
                             }
                             __syncwarp();
-                            int8_t *g0 = p.feats + (gbyte - (unsigned long long)sp0);        // 16-byte aligned
+                            int8_t *g0 = f_g16 + (rb - sp0);                                 // 16-byte aligned
                             const int e0 = send & ~15;
                             if (lane < 16) {
                                 if (sp0 > 0 && lane >= sp0 && lane < send) g0[lane] = (int8_t)rst[lane];
                                 if ((e0 > 0 || sp0 == 0) && e0 + lane < send) g0[e0 + lane] = (int8_t)rst[e0 + lane];
                             }
                             __syncwarp();
-                            const int c0f = sp0 > 0 ? 1 : 0, c1f = send >> 4, nch = (send + 15) >> 4;
-                            for (int c = lane; c < nch; c += 32) {
-                                const uint4 v = *reinterpret_cast<const uint4 *>(rst + 16 * c);
-                                *reinterpret_cast<uint4 *>(rst + 16 * c) = make_uint4(0, 0, 0, 0);
-                                if (c >= c0f && c < c1f) *reinterpret_cast<uint4 *>(g0 + 16 * c) = v;
+                            // (52 chunks at most: lane t takes chunks t and t + 32)
+                            const int c0f = sp0 > 0 ? 1 : 0, c1f = send >> 4;
+                            {
+                                const uint4 va = *reinterpret_cast<const uint4 *>(rst + 16 * lane);
+                                *reinterpret_cast<uint4 *>(rst + 16 * lane) = make_uint4(0, 0, 0, 0);
+                                if (lane >= c0f && lane < c1f) *reinterpret_cast<uint4 *>(g0 + 16 * lane) = va;
+                                if (lane + 32 < FSTAGE / 16) {
+                                    const uint4 vb = *reinterpret_cast<const uint4 *>(rst + 16 * (lane + 32));
+                                    *reinterpret_cast<uint4 *>(rst + 16 * (lane + 32)) = make_uint4(0, 0, 0, 0);
+                                    if (lane + 32 < c1f) *reinterpret_cast<uint4 *>(g0 + 16 * (lane + 32)) = vb;
+                                }
                             }
                             __syncwarp();
                         }
@@ -1496,6 +1513,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
     for (int k = 0;; ++k) {
         const int s = k & 1;
         if (tile_cur < ntiles_i) {
+            build_map((long long)tile_cur * NW + cw);
             if (s == 0 ? pending[0] : pending[1]) wait_window(s, phase_bits);
             __syncwarp();
             PROF5(0);
