@@ -375,10 +375,12 @@ static int run_device(latok_b200_engine *e, Batch &b)
     // the matrix mode runs the v4 kernel (one CTA per 7 936-byte tile); everything else (split mask, spans, token
     // features) runs v5 (one warp per range, a tile = the ranges of one CTA) in one of its two geometries: short strings
     // (3 KB ranges, 11 compute warps per CTA) or long strings (4 KB ranges, 9 warps: fewer range boundaries inside
-    // space-free runs), by the average string length of the batch (LATOK_B200_GEOMETRY=short|long overrides)
+    // space-free runs), by the average string length of the batch; token features: always the long one
+    // (LATOK_B200_GEOMETRY=short|long overrides)
     const bool words = (b.what & LATOK_B200_MATRIX) != 0, feats = (b.what & LATOK_B200_FEATS) != 0;
     const bool use5 = !words && !getenv("LATOK_B200_FORCE_V4");
     bool shortg = b.n_bytes < 4096LL * (b.n_strings > 0 ? b.n_strings : 1);
+    if (feats) shortg = false;      // the token-feature instantiation lives on registers (25 planes per lane): 96 beat 24 warps per SM
     if (const char *g = getenv("LATOK_B200_GEOMETRY")) shortg = g[0] == 's';
     const int range5 = shortg ? tokenize5_range_bytes_short() : tokenize5_range_bytes();
     const int nw5 = shortg ? tokenize5_ranges_per_tile_short() : tokenize5_ranges_per_tile();

@@ -1255,10 +1255,13 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                     acc[4] = vadd(acc[4], b.x); acc[5] = vadd(acc[5], b.y); acc[6] = vadd(acc[6], b.z);
                 };
                 // open tails of the lanes below `t`, then of the steps before (fc*), then of the ranges before (osum chain)
+                // (a tail holds at most 32 of a feature and so does the part summed so far: the first six additions cannot carry
+                // from one byte into the next and are plain ones)
                 auto walk_lanes = [&](int t, unsigned acc[7], bool &hit) {
-                    for (; t >= 0 && !hit; --t) {
+                    for (int it = 0; t >= 0 && !hit; --t, ++it) {
                         const uint4 a = *reinterpret_cast<const uint4 *>(tailsS + t * 8), b = *reinterpret_cast<const uint4 *>(tailsS + t * 8 + 4);
-                        add8(acc, a, b);
+                        if (it < 6) { acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; }
+                        else add8(acc, a, b);
                         hit = b.w != 0u;
                     }
                     if (!hit) {
@@ -1409,9 +1412,10 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 {
                     unsigned acc[7] = {0, 0, 0, 0, 0, 0, 0};
                     bool hit = false;
-                    for (int t = 31; t >= 0 && !hit; --t) {
+                    for (int t = 31, it = 0; t >= 0 && !hit; --t, ++it) {
                         const uint4 a = *reinterpret_cast<const uint4 *>(tailsS + t * 8), b = *reinterpret_cast<const uint4 *>(tailsS + t * 8 + 4);
-                        add8(acc, a, b);
+                        if (it < 7) { acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; }
+                        else add8(acc, a, b);
                         hit = b.w != 0u;
                     }
                     if (!hit) { add8(acc, make_uint4(fc[0], fc[1], fc[2], fc[3]), make_uint4(fc[4], fc[5], fc[6], 0u)); hit = fc_hit; }
