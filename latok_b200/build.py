@@ -93,7 +93,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     nvcc = find_nvcc()
     with tempfile.TemporaryDirectory() as tmp:
         jobs = [(src, [], Path(tmp) / (src.stem + ".o")) for src in SOURCES]
-        jobs.append((CSRC / "latok_tok5.cu", SHORT_DEFS, Path(tmp) / "latok_tok5_short.o"))
+        short_defs = os.environ["LATOK_SHORT_DEFS"].split() if os.environ.get("LATOK_SHORT_DEFS") else SHORT_DEFS     # (experiments)
+        jobs.append((CSRC / "latok_tok5.cu", short_defs, Path(tmp) / "latok_tok5_short.o"))
 
         def compile_one(job):
             src, defs, obj = job

@@ -1111,6 +1111,14 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 }
                 __syncwarp();
             }
+            // (token-feature mode: the 25 feature planes of the lane-word, parked in HBM by pass A -- asked for here, used after
+            // the spans, so that the L2 latency is covered)
+            uint32_t Q[kFeats ? NFEAT : 1];
+            if (kFeats) {
+                const uint32_t *pl = p.planes + (((size_t)r * RS + js) * NFEAT) * 32 + lane;
+#pragma unroll
+                for (int f = 0; f < NFEAT; ++f) Q[f] = pl[f * 32];
+            }
             // ------------------------------------------------------------ token spans
             // latest owned string start in the lanes before this one (else: the one open when the step began)
             const uint32_t FO = Fm & OWN;
@@ -1225,12 +1233,6 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                 // Every split that follows a non-space character ends a token; the lane that holds it sums the token's
                 // characters back to its first one (a split): population counts of the 25 feature planes over the part
                 // inside this lane-word, then the open tails of the lanes / steps / ranges before it.
-                uint32_t Q[NFEAT];
-                {
-                    const uint32_t *pl = p.planes + (((size_t)r * RS + js) * NFEAT) * 32 + lane;
-#pragma unroll
-                    for (int f = 0; f < NFEAT; ++f) Q[f] = pl[f * 32];
-                }
                 auto plane_sums = [&](uint32_t frag, unsigned acc[7]) {
 #pragma unroll
                     for (int f = 0; f < NFEAT; ++f) acc[f >> 2] += (unsigned)__popc(Q[f] & frag) << (8 * (f & 3));   // <= 32 each: no carry
