@@ -65,7 +65,7 @@ constexpr int SSTAGE = 5 * 36 * 4;          // pass D: bit stage (up to 5 value 
 constexpr int TCAP = 320;                // tokens staged per step; steps with more write their pairs directly
 constexpr int TSTAGE = (TCAP + 2) * 8;
 constexpr int FLIST = 512;               // token-feature mode: token ends per step that are written in the order of their ordinals
-constexpr int FSTAGE = 832;              // ... row stage of one trip: 15 + 32 * 25 bytes, in 16-byte chunks
+constexpr int FSTAGE = 832;              // ... row stage: up to 15 bytes left of the trip before + 32 * 25 bytes, in 16-byte chunks
 constexpr int TWG = 12;                  // generic rules: words per lane-word in the (separate) state buffers
 enum { BAR_AGG = 1, BAR_PRE = 3 };
 static_assert(RANGE == WIN - HALO && HALO % 32 == 0 && RANGE % 16 == 0, "geometry");
@@ -1314,6 +1314,13 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                         __syncwarp();
                         // (2) the rows that may be written (row capacity of the caller's array; no row in front of the first token)
                         const int jlo = max(0, f_kmin - kr0), jhi = min(nrows, f_kmax - kr0);
+                        // (3) the rows of the step are consecutive bytes of the array, one stream: stream offset x <-> gS + x, the
+                        // stage holds the stream from offset gw (a multiple of 16) on, the rows of the next trip begin at stage
+                        // position sp < 16
+                        const int rb0 = f_ph16 + NFEAT * (kr0 + jlo);                       // first byte of the step's rows, from f_g16
+                        int8_t *gS = f_g16 + (rb0 & ~15);
+                        const int head = rb0 & 15;                                          // bytes of the first chunk that belong to the rows before
+                        int sp = head, gw = 0;
                         for (int jb = jlo; jb < jhi; jb += 32) {
                             const int j = jb + lane;
                             const bool valid = j < jhi;
@@ -1326,14 +1333,11 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                             for (int f = 0; f < NFEAT; ++f)
                                 acc[f >> 2] += (unsigned)__popc(__shfl_sync(FULL, Q[f], w) & frag) << (8 * (f & 3));
                             if (valid && !hit) walk_lanes(w - 1, acc, hit);
-                            // (3) the 32 rows are consecutive bytes of the array: staged at their byte phase inside a 16-byte
-                            // chunk, they leave as whole chunks; the bytes of the first and the last chunk that belong to this
-                            // trip go singly (their neighbours are written by another trip / step / warp)
-                            const int rb = f_ph16 + NFEAT * (kr0 + jb);                     // first byte of the trip's rows, from f_g16
-                            const int sp0 = rb & 15;
-                            const int nv = min(32, jhi - jb), send = sp0 + NFEAT * nv;
+                            // the 32 rows of the trip, staged at their byte phase: five plain word stores per row, the two words a
+                            // row shares with its neighbours by atomicOr
+                            const int nv = min(32, jhi - jb), send = sp + NFEAT * nv;
                             if (valid) {
-                                const int pb = sp0 + NFEAT * lane;
+                                const int pb = sp + NFEAT * lane;
                                 const uint32_t S = 8u * (uint32_t)(pb & 3);
                                 uint32_t *wq = reinterpret_cast<uint32_t *>(rst) + (pb >> 2);
                                 atomicOr(wq, acc[0] << S);                                   // (shares its word with the row before)
@@ -1343,26 +1347,27 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
                                 atomicOr(wq + 6, __funnelshift_l(acc[5], acc[6], S));       // (... with the row after)
                             }
                             __syncwarp();
-                            int8_t *g0 = f_g16 + (rb - sp0);                                 // 16-byte aligned
-                            const int e0 = send & ~15;
+                            // whole 16-byte chunks leave as such; what is left of the stream (< 16 bytes) moves to the front of the
+                            // stage for the next trip.  Only the step's first chunk (when the rows before end inside it) and its
+                            // last one are shared with another step / warp: their bytes go singly.
+                            const bool firstt = jb == jlo, lastt = jb + 32 >= jhi;
+                            const int nfull = send >> 4, e0 = send & ~15;
+                            const bool head_part = firstt && head > 0;
                             if (lane < 16) {
-                                if (sp0 > 0 && lane >= sp0 && lane < send) g0[lane] = (int8_t)rst[lane];
-                                if ((e0 > 0 || sp0 == 0) && e0 + lane < send) g0[e0 + lane] = (int8_t)rst[e0 + lane];
+                                if (head_part && lane >= head && lane < send) gS[lane] = (int8_t)rst[lane];
+                                if (lastt && !(head_part && e0 == 0) && e0 + lane < send) gS[gw + e0 + lane] = (int8_t)rst[e0 + lane];
                             }
+                            const uint4 zero4 = make_uint4(0, 0, 0, 0);
+                            const uint4 va = *reinterpret_cast<const uint4 *>(rst + 16 * lane);
+                            const uint4 vb = lane + 32 < FSTAGE / 16 ? *reinterpret_cast<const uint4 *>(rst + 16 * (lane + 32)) : zero4;
+                            const uint4 vr = (lane == 0 && !lastt) ? *reinterpret_cast<const uint4 *>(rst + 16 * nfull) : zero4;
                             __syncwarp();
-                            // (52 chunks at most: lane t takes chunks t and t + 32)
-                            const int c0f = sp0 > 0 ? 1 : 0, c1f = send >> 4;
-                            {
-                                const uint4 va = *reinterpret_cast<const uint4 *>(rst + 16 * lane);
-                                *reinterpret_cast<uint4 *>(rst + 16 * lane) = make_uint4(0, 0, 0, 0);
-                                if (lane >= c0f && lane < c1f) *reinterpret_cast<uint4 *>(g0 + 16 * lane) = va;
-                                if (lane + 32 < FSTAGE / 16) {
-                                    const uint4 vb = *reinterpret_cast<const uint4 *>(rst + 16 * (lane + 32));
-                                    *reinterpret_cast<uint4 *>(rst + 16 * (lane + 32)) = make_uint4(0, 0, 0, 0);
-                                    if (lane + 32 < c1f) *reinterpret_cast<uint4 *>(g0 + 16 * (lane + 32)) = vb;
-                                }
-                            }
+                            *reinterpret_cast<uint4 *>(rst + 16 * lane) = vr;                // (lane 0: the remainder; zero everywhere else)
+                            if (lane + 32 < FSTAGE / 16) *reinterpret_cast<uint4 *>(rst + 16 * (lane + 32)) = zero4;
+                            if (lane >= (head_part ? 1 : 0) && lane < nfull) *reinterpret_cast<uint4 *>(gS + gw + 16 * lane) = va;
+                            if (lane + 32 < nfull) *reinterpret_cast<uint4 *>(gS + gw + 16 * (lane + 32)) = vb;
                             __syncwarp();
+                            gw += 16 * nfull; sp = send & 15;
                         }
                     } else if (nrows > 0) {
                     // (more token ends in one step than the list holds: every lane writes the rows of its own token ends as one

@@ -2,7 +2,7 @@
 alignments when they are laid end to end -- the kind of input that exposed the token-end bug fixed in round 1
 (test_gpu_parity.py::test_token_covering_a_whole_range).  First run on a B200 in round 2 (12 passed); part of the
 `gpu` suite since.  Also here: tokens that span two or more whole ranges / a tile boundary (spans only and with token
-features), a pre-sized token buffer that is too small (the cap_tokens direct path + the re-run), the in-library
+features), token-feature rows in the order of their ordinals (dense, sparse, > 512 per step), a pre-sized token buffer that is too small (the cap_tokens direct path + the re-run), the in-library
 pipeline (depth 2), compact 16-bit spans, and the UCD-15 library check.
 """
 import os
@@ -94,6 +94,31 @@ def test_tokens_spanning_whole_ranges_and_tiles(engine):
             texts.append("日" * (n // 3) + " z")
     check_batch(engine, texts, 3, label="long tokens, spans")
     check_batch(engine, texts, 7, label="long tokens, token features")
+
+
+def test_token_feature_rows_in_ordinal_order(engine):
+    """Token-feature rows are written in the order of the token ordinals, 32 per trip, staged at their byte phase
+    (latok_tok5.cu, token-feature mode): steps with few, many and more than 512 token ends (the per-lane fallback),
+    the 25-byte rows at every phase of a 16-byte chunk, tokens longer than 255 characters (uint8 wrap-around of the
+    sums, latok.c:342-354), tokens that begin several lane-words / steps / ranges before they end."""
+    RANGE, _ = engine.geometry
+    texts = []
+    for k in range(48):
+        lead = "w " * k                                  # k tokens in front: the rows of what follows start at every phase
+        texts.append(lead + "a,b" * 700)                 # one token end per character: > 512 per 1 KB step (fallback path)
+        texts.append(lead + "!?" * (300 + 7 * k))        # symbols only
+        texts.append(lead + "ab cd, " * (140 + k))       # ordinary density, ~170 rows per step
+        texts.append(lead + ("x" * (250 + k) + " ") * 9) # tokens around the uint8 wrap (250..297 characters)
+        texts.append(lead + "é" * (260 + 3 * k) + " 日本語 " + "y" * (1000 + 37 * k) + " z")
+        texts.append(lead + "tok " * 3 + "q" * (RANGE + 100 * k) + ",end")     # a token that began a range earlier
+        texts.append("z" * k)                            # a few bytes, also the empty string
+    check_batch(engine, texts, 7, label="token-feature rows")
+    # exactly around the list capacity: 505..520 token ends in the first step of a string, then sparse text
+    texts = [(",a" * (250 + j) + " " + "word " * 300) for j in range(0, 12)]
+    check_batch(engine, texts, 7, label="token-feature rows around the list capacity")
+    # one token / a handful of tokens per batch (the trip's first and last chunk are the same one)
+    for t in (["a"], ["a b"], ["a b c d e f"], ["", "a", "", "b c"]):
+        check_batch(engine, t, 7, label=f"token-feature rows, tiny batch {t!r}")
 
 
 def test_small_presized_token_buffer(engine):
