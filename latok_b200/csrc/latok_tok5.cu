@@ -17,8 +17,10 @@
 //   pass C  backward over the steps: blank the chunks whose closer is hot, split values
 //           (default_tokenizer.py:121-132), token flags (default_tokenizer.py:148-158), counts
 //   -> the service warp sums the ranges of the tile, publishes the aggregate, looks back, hands the prefix down
-//   pass D  forward: split bytes and (start,end) pairs staged per step in shared memory and written with
-//           aligned 16-byte stores; CSR offsets by one lane per string.
+//   pass D  CSR offsets by one lane per string; then forward over the steps: split bytes and (start,end) pairs staged
+//           per step in shared memory and written with aligned 16-byte stores; in the token-feature instantiation the
+//           rows of the step's tokens in the order of their ordinals (lane t sums row 32 i + t from the planes of the
+//           lane-word the token ended in, fetched by shuffle), staged and written as whole 16-byte chunks.
 // Rare paths, one mechanism (resolve()): every range posts, with its counts, how it transforms a block-mask backlog
 // (x -> max(x + u, f0): u = marks - closers, f0 = what it leaves when nothing enters), the marks in front of its first
 // closer and whether it begins / ends at a chunk closer.  The service warp composes these over the ranges of the tile:
@@ -376,11 +378,7 @@ __global__ void __launch_bounds__(NTH, kDefault ? LATOK_V5_CTAS : 1) tokenize5_k
         int crun = 0;                    // characters of the range so far
         int xb = x_init;                 // block-mask backlog entering the next step (regular evaluation; 0 almost always)
 
-#ifdef LATOK_V5_UNROLL_A
-#pragma unroll 2
-#else
 #pragma unroll 1
-#endif
         for (int j = 0; j <= RS; ++j) {
             // -------------------------------------------------------------- base planes of step j
             uint32_t Pc[NBASE], Fc = 0, leadc = 0; int nc = 0, c0c = 0;
